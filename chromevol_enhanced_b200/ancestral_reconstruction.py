@@ -1,0 +1,520 @@
+"""Drop-in for the likelihood classes of the reference's ``src/ancestral_reconstruction.py``.
+
+Same class names, constructor arguments, method signatures, attributes, mutation and error
+behaviour as the reference; the numpy/scipy bodies are replaced by calls into
+the sm_100a kernels (``chromevol_enhanced_b200/csrc``) through the C ABI in
+``include/chromevol_b200.h``.  There is no CPU fallback: without a B200 these classes raise.
+
+Reference lines are cited as AR:<line>.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import scipy.optimize as opt
+import torch
+
+from . import _lib
+from .engine import (LikelihoodEngine, params_to_row, rate_matrix, transition_matrices)
+from .flatten import FlatTree
+
+# AR:22
+MODEL_PARAMETER_NAMES = ['gain', 'loss', 'dupl', 'demidupl_gain', 'demidupl_loss',
+                         'base_number_gain', 'base_number_loss', 'linear_rate']
+
+# AR:602-604
+EVENT_TYPES = ['gain', 'loss', 'duplication', 'base_number_gain', 'base_number_loss',
+               'demi_gain_like', 'demi_loss_like', 'other']
+
+
+class ChromEvolutionModel:
+    """Parameter container + rate matrix + transition probabilities (AR:24-166)."""
+
+    def __init__(self, max_chromosome_number=50, model_type='full', custom_params=None):
+        self.max_chr = max_chromosome_number
+        self.model_type = model_type
+        self.params = {                                                   # AR:38-48
+            'gain': 0.1, 'loss': 0.1, 'dupl': 0.05,
+            'demidupl_gain': 0.01, 'demidupl_loss': 0.01,
+            'base_number': None, 'base_number_gain': 0.01, 'base_number_loss': 0.01,
+            'linear_rate': 0.01,
+        }
+        if custom_params:
+            self.params.update(custom_params)
+        self.branch_params = {}
+        self.Q_matrix = None
+        self.transition_probs = {}
+
+    def set_parameters(self, **kwargs):
+        """Unknown keys are ignored, like AR:59-65."""
+        for key, value in kwargs.items():
+            if key in self.params:
+                self.params[key] = value
+
+    def set_branch_parameters(self, branch_id, **kwargs):
+        """AR:67-73."""
+        if branch_id not in self.branch_params:
+            self.branch_params[branch_id] = self.params.copy()
+        for key, value in kwargs.items():
+            if key in self.branch_params[branch_id]:
+                self.branch_params[branch_id][key] = value
+
+    def build_transition_rate_matrix(self, params=None):
+        """Q over states 0..max_chr from the rate-matrix kernel (bit-identical to AR:75-134)."""
+        current = params if params is not None else self.params
+        Q = rate_matrix(params_to_row(current), self.max_chr + 1)[0]
+        self.Q_matrix = Q
+        return Q
+
+    def get_transition_probabilities(self, branch_length, params=None):
+        """P(t) = expm(Q t), floored at 1e-12 and row-normalised (AR:136-166)."""
+        current = params if params is not None else self.params
+        n = self.max_chr + 1
+        if branch_length < 0:                                             # AR:143-145
+            logging.warning(f"Negative branch length {branch_length} encountered. Using 0.0 instead.")
+            branch_length = 0.0
+        if branch_length == 0:                                            # AR:146-148
+            self.Q_matrix = self.build_transition_rate_matrix(current)
+            return np.eye(n)
+        P, _, _, flags = transition_matrices(params_to_row(current), [branch_length], n,
+                                             return_info=True)
+        if int(flags[0, 0]) & 2:                                          # AR:156-159
+            logging.error(f"NaNs in transition probability matrix for branch length "
+                          f"{branch_length}. Params: {current}")
+        return np.ascontiguousarray(P[0, 0])
+
+
+class ChromEvolLikelihoodCalculator:
+    """Felsenstein pruning on the device (AR:168-322)."""
+
+    def __init__(self, tree, chromosome_data, model):
+        self.tree = tree
+        self.data = chromosome_data
+        self.model = model
+        self.likelihoods = {}
+        self.root_frequencies = None
+        self._flat = None
+        self._flat_key = None
+        self._engine = None
+        self._last_logl = None
+
+    # -- device state ---------------------------------------------------------------------
+    def refresh(self):
+        """Drop the cached flattened tree (call after editing the tree or the counts dict)."""
+        self._flat = None
+        self._engine = None
+        self.likelihoods = {}
+
+    def _device_engine(self):
+        key = (id(self.tree), id(self.data), len(self.data) if self.data is not None else 0,
+               self.model.max_chr)
+        if self._engine is None or self._flat_key != key:
+            self._flat = FlatTree(self.tree, self.data, self.model.max_chr)
+            self._engine = LikelihoodEngine(self._flat)
+            self._flat_key = key
+        return self._engine
+
+    def _has_branch_params(self):
+        return bool(self.model.branch_params)
+
+    def set_root_frequencies(self, frequencies):
+        """AR:180-186."""
+        n = self.model.max_chr + 1
+        if frequencies is not None and len(frequencies) == n:
+            self.root_frequencies = frequencies / np.sum(frequencies)
+        else:
+            logging.warning("Invalid root frequencies provided or length mismatch. Using uniform "
+                            f"distribution. Expected length {n}, got "
+                            f"{len(frequencies) if frequencies is not None else 'None'}")
+            self.root_frequencies = np.ones(n) / n
+
+    def _up_pass(self):
+        """One device evaluation; fills ``likelihoods`` (id(node) -> ndarray) like the memo dict."""
+        if self._has_branch_params():
+            raise NotImplementedError(
+                "branch-specific parameters (set_branch_parameters) are not on the device path "
+                "yet (SURVEY.md section 8 row f4)")
+        if self.root_frequencies is None:
+            self.set_root_frequencies(None)
+        eng = self._device_engine()
+        logl = eng.log_likelihood(params_to_row(self.model.params)[None, :],
+                                  root_freq=self.root_frequencies)
+        vec = eng.node_vectors(0).cpu().numpy()
+        self.likelihoods = {id(nd): vec[k] for k, nd in enumerate(self._flat.nodes)}
+        self._last_logl = float(logl[0].item())
+        return self._last_logl
+
+    def calculate_likelihood_at_node(self, node):
+        """Conditional likelihood vector of ``node`` (AR:189-249)."""
+        if id(node) not in self.likelihoods:
+            self._up_pass()
+        return self.likelihoods[id(node)]
+
+    def calculate_total_log_likelihood(self):
+        """AR:251-272.  A populated memo short-circuits like AR:195-197 does for the root."""
+        root = self.tree.get_tree_root()
+        if self.root_frequencies is None:
+            self.set_root_frequencies(None)
+        if id(root) in self.likelihoods and self.likelihoods:
+            total = np.sum(self.likelihoods[id(root)] * self.root_frequencies)
+            return -np.inf if total <= 0 else np.log(total)
+        return self._up_pass()
+
+    def log_likelihood_batch(self, params_matrix, names=None):
+        """Additive API: logL for many parameter vectors in one launch sequence.
+
+        ``params_matrix`` is (B, len(names)); unnamed parameters stay at ``model.params``.
+        Returns a numpy array (B,).  Does not touch ``model.params`` or the memo.
+        """
+        names = list(names) if names is not None else MODEL_PARAMETER_NAMES
+        if self.root_frequencies is None:
+            self.set_root_frequencies(None)
+        base = params_to_row(self.model.params)
+        X = np.atleast_2d(np.asarray(params_matrix, dtype=np.float64))
+        rows = np.tile(base, (X.shape[0], 1))
+        order = {nm: k for k, nm in enumerate(MODEL_PARAMETER_NAMES + ['base_number'])}
+        for j, nm in enumerate(names):
+            rows[:, order[nm]] = X[:, j]
+        eng = self._device_engine()
+        return eng.log_likelihood(rows, root_freq=self.root_frequencies).cpu().numpy()
+
+    def ancestral_state_reconstruction(self):
+        """argmax of the normalised up-pass vector at every node (AR:274-322)."""
+        if not self.likelihoods:
+            self.calculate_total_log_likelihood()
+        eng = self._device_engine()
+        flat = self._flat
+        # the vectors of the last evaluation are still resident; recompute if the memo came from
+        # somewhere else
+        if any(id(nd) not in self.likelihoods for nd in flat.nodes):
+            self._up_pass()
+        ml_count, ml_prob, probs = eng.ancestral_states(0, want_probs=True)
+        ml_count = ml_count.cpu().numpy()
+        ml_prob = ml_prob.cpu().numpy()
+        probs = probs.cpu().numpy()
+        for node in self.tree.traverse("preorder"):                       # AR:298
+            k = flat.index.get(id(node))
+            if k is None or id(node) not in self.likelihoods:
+                continue
+            node.add_features(ml_count=np.int64(ml_count[k]))
+            node.add_features(ml_probability=np.float64(ml_prob[k]))
+            node.add_features(state_probabilities=probs[k].copy())
+        return self.tree
+
+
+class ChromEvolOptimizer:
+    """Negative log-likelihood objective + L-BFGS-B driver (AR:325-426)."""
+
+    DEFAULT_PARAM_NAMES = [p for p in MODEL_PARAMETER_NAMES if p not in ['base_number']]
+
+    def __init__(self, tree, chromosome_data, model):
+        self.tree = tree
+        self.data = chromosome_data
+        self.model = model
+        self.calculator = ChromEvolLikelihoodCalculator(self.tree, self.data, self.model)
+        self.batched_gradient = False   # additive: evaluate the k+1 finite-difference points as one batch
+
+    def objective_function(self, params_vector, param_names_to_optimize):
+        """AR:341-371: clamps, mutates model.params, clears the memo, penalties 1e9 / 1e10."""
+        try:
+            update = {}
+            for i, name in enumerate(param_names_to_optimize):
+                if name != 'linear_rate':
+                    update[name] = max(params_vector[i], 1e-7)
+                else:
+                    update[name] = params_vector[i]
+            self.model.set_parameters(**update)
+            self.calculator.likelihoods = {}
+            log_likelihood = self.calculator.calculate_total_log_likelihood()
+            if np.isinf(log_likelihood) or np.isnan(log_likelihood):
+                return 1e9
+            return -log_likelihood
+        except Exception as e:  # noqa: BLE001 - the reference swallows everything here
+            logging.error(f"Error in objective function: {e} with params {params_vector}")
+            return 1e10
+
+    # -- additive: batched value + forward-difference gradient --------------------------------
+    def _clamped_rows(self, X, names):
+        X = np.array(X, dtype=np.float64, copy=True)
+        for j, nm in enumerate(names):
+            if nm != 'linear_rate':
+                X[:, j] = np.maximum(X[:, j], 1e-7)
+        return X
+
+    def objective_batch(self, X, names):
+        """-logL for every row of X (B, k) in one device batch; same clamps/penalties as AR:341-371,
+        without mutating the model."""
+        ll = self.calculator.log_likelihood_batch(self._clamped_rows(np.atleast_2d(X), names), names)
+        out = -ll
+        out[~np.isfinite(ll)] = 1e9
+        return out
+
+    def value_and_gradient(self, x, names, bounds, eps=1e-8):
+        """f(x) and scipy's '2-point' forward-difference gradient (step eps, flipped to a
+        backward step where x + eps would leave the bounds) from ONE batch of k+1 evaluations."""
+        x = np.asarray(x, dtype=np.float64)
+        k = x.size
+        pts = np.tile(x, (k + 1, 1))
+        steps = np.full(k, eps)
+        for i, (lo, hi) in enumerate(bounds):
+            if hi is not None and x[i] + eps > hi:
+                steps[i] = -eps
+        for i in range(k):
+            pts[i + 1, i] = x[i] + steps[i]
+        f = self.objective_batch(pts, names)
+        grad = (f[1:] - f[0]) / ((pts[np.arange(1, k + 1), np.arange(k)]) - x)
+        return float(f[0]), grad
+
+    def optimize_parameters(self, method='L-BFGS-B', maxiter=1000, params_to_optimize=None):
+        """AR:373-426."""
+        if params_to_optimize is None:
+            params_to_optimize = self.DEFAULT_PARAM_NAMES
+        valid = [p for p in params_to_optimize
+                 if p in self.model.params and isinstance(self.model.params[p], (int, float))]
+        x0 = [self.model.params[p] for p in valid]
+        bounds = []
+        for p in valid:
+            if p == 'linear_rate':
+                bounds.append((-1.0, 1.0))
+            elif p == 'base_number':
+                continue
+            else:
+                bounds.append((1e-7, 10.0))
+        logging.info(f"Optimizing model parameters using {method} for: {valid}")
+        logging.info(f"Initial parameters: {dict(zip(valid, x0))}")
+        if not x0:
+            logging.warning("No parameters to optimize.")
+            return None
+
+        if self.batched_gradient and method == 'L-BFGS-B':
+            def fun(x):
+                f, g = self.value_and_gradient(x, valid, bounds)
+                return f, g
+            result = opt.minimize(fun, np.array(x0), jac=True, method=method, bounds=bounds,
+                                  options={'maxiter': maxiter, 'disp': False})
+        else:
+            result = opt.minimize(self.objective_function, np.array(x0), args=(valid,),
+                                  method=method, bounds=bounds,
+                                  options={'maxiter': maxiter, 'disp': False})
+
+        if result.success:
+            final = dict(zip(valid, result.x))
+            self.model.set_parameters(**final)
+            logging.info("Optimization successful!")
+            logging.info(f"Optimized parameters: { {k: f'{v:.4f}' for k, v in final.items()} }")
+            logging.info(f"Final log-likelihood: {-result.fun:.4f}")
+            return result
+        logging.error(f"Optimization failed: {result.message}")
+        return None
+
+
+class StochasticMapper:
+    """Forward stochastic mapping of events down the tree (AR:428-644), Philox on the device."""
+
+    def __init__(self, tree, model, num_mappings=100, seed=None):
+        self.tree = tree
+        self.model = model
+        self.num_mappings = num_mappings
+        self.seed = seed
+        self.n_bins = 256
+
+    def _classify_event(self, from_state, to_state, params):
+        """AR:441-464 (host helper; the kernel applies the same rules per event)."""
+        if to_state == from_state + 1:
+            return 'gain'
+        if to_state == from_state - 1:
+            return 'loss'
+        if to_state == 2 * from_state and from_state > 0:
+            return 'duplication'
+        base_num = params.get('base_number')
+        if base_num and base_num > 0:
+            if to_state == from_state + base_num:
+                return 'base_number_gain'
+            if to_state == from_state - base_num:
+                return 'base_number_loss'
+        delta = to_state - from_state
+        if delta > 1 and delta < from_state:
+            return 'demi_gain_like'
+        if delta < -1 and abs(delta) < from_state / 2:
+            return 'demi_loss_like'
+        return 'other'
+
+    def _draw_seed(self):
+        if self.seed is not None:
+            return int(self.seed)
+        # the reference draws from the global numpy state (AR:489); keep that dependence
+        return int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
+
+    def simulate_events_on_branch(self, start_state, branch_length, params):
+        """One branch, one replicate, as a list of event dicts + end state (AR:467-521).
+
+        Event times are not retained by the device histogram path, so this host-facing helper
+        runs a one-node tree through the same kernel and reports counts as untimed events."""
+        from .mapper import simulate_single_branch
+        return simulate_single_branch(self, start_state, branch_length, params)
+
+    def perform_stochastic_mapping(self):
+        """AR:523-590: returns {id(node): {type: {mean,std,ci_lower,ci_upper,total_occurrences}}}
+        and annotates nodes with expected_<type>."""
+        from .mapper import run_stochastic_mapping
+        logging.info(f"Performing stochastic mapping with {self.num_mappings} replicates...")
+        self.event_counts_summary = run_stochastic_mapping(self)
+        for node in self.tree.traverse():
+            if not node.is_root() and id(node) in self.event_counts_summary:
+                for etype, metrics in self.event_counts_summary[id(node)].items():
+                    node.add_features(**{f"expected_{etype}": metrics['mean']})
+        return self.event_counts_summary
+
+    def _summarize_event_counts(self, all_branch_mappings_across_replicates):
+        """AR:593-644 for explicit per-replicate event lists (host; used by the CSV writer hack
+        at AR:1116 with an empty dict)."""
+        summary = {}
+        for branch_id, mappings in all_branch_mappings_across_replicates.items():
+            per_type = {et: [] for et in EVENT_TYPES}
+            for events in mappings:
+                c = {et: 0 for et in EVENT_TYPES}
+                for ev in events:
+                    if ev['type'] in c:
+                        c[ev['type']] += 1
+                for et in EVENT_TYPES:
+                    per_type[et].append(c[et])
+            out = {}
+            for et, counts in per_type.items():
+                if counts:
+                    out[et] = {'mean': np.mean(counts), 'std': np.std(counts),
+                               'ci_lower': np.percentile(counts, 2.5),
+                               'ci_upper': np.percentile(counts, 97.5),
+                               'total_occurrences': np.sum(counts)}
+                else:
+                    out[et] = {'mean': 0, 'std': 0, 'ci_lower': 0, 'ci_upper': 0,
+                               'total_occurrences': 0}
+            summary[branch_id] = out
+        return summary
+
+
+# ------------------------------------------------------------------------------------------
+def perform_chromevol_analysis(tree, counts_dict, max_chr_num, root_prior_state=None, use_ml=True,
+                               optimize_params=True, stochastic_mapping=True,
+                               model_params_input=None):
+    """AR:648-735."""
+    logging.info("\n--- ChromEvol-Inspired Maximum Likelihood Analysis ---")
+    model = ChromEvolutionModel(max_chromosome_number=max_chr_num, model_type='full',
+                                custom_params=model_params_input)
+    max_obs = 0
+    for leaf in tree:
+        if leaf.name in counts_dict:
+            count = counts_dict[leaf.name]
+            leaf.add_features(count=count)
+            if count is not None:
+                max_obs = max(max_obs, count)
+        else:
+            leaf.add_features(count=None)
+            logging.warning(f"No chromosome count for species {leaf.name} in input file.")
+    if max_obs > model.max_chr:
+        logging.warning(f"Max observed chromosome count ({max_obs}) > model.max_chr "
+                        f"({model.max_chr}). Consider increasing max_chr_num.")
+    if not use_ml:
+        logging.info("use_ml=False, skipping ML-based analysis and stochastic mapping.")
+        return model, tree
+
+    calculator = ChromEvolLikelihoodCalculator(tree, counts_dict, model)
+    n = model.max_chr + 1
+    if root_prior_state is not None and 0 <= root_prior_state <= model.max_chr:
+        logging.info(f"Setting strong prior for root state = {root_prior_state}")
+        root_freq = np.zeros(n)
+        root_freq[root_prior_state] = 1.0
+    else:
+        logging.info("Using uniform prior for root state frequencies.")
+        root_freq = np.ones(n) / n
+    calculator.set_root_frequencies(root_freq)
+
+    if optimize_params:
+        optimizer = ChromEvolOptimizer(tree, counts_dict, model)
+        optimizer.calculator = calculator
+        result = optimizer.optimize_parameters()
+        if not result or not result.success:
+            logging.error("Parameter optimization failed. Continuing with initial/default parameters.")
+
+    calculator.likelihoods = {}
+    final_ll = calculator.calculate_total_log_likelihood()
+    logging.info(f"Final log-likelihood with current parameters: {final_ll:.4f}")
+    calculator.ancestral_state_reconstruction()
+    for node in tree.traverse():
+        if hasattr(node, 'ml_count'):
+            node.add_features(count=node.ml_count)
+
+    if stochastic_mapping:
+        mapper = StochasticMapper(tree, model, num_mappings=100)
+        mapper.perform_stochastic_mapping()
+        logging.info("\n--- Expected Number of Events per Branch (Stochastic Mapping Summary) ---")
+        for node in tree.traverse():
+            if not node.is_root() and hasattr(node, 'expected_gain'):
+                summary = mapper.event_counts_summary.get(id(node), {})
+                parts = [f"{et}={m['mean']:.2f}" for et, m in summary.items() if m['mean'] > 0.01]
+                if parts:
+                    name = node.name if node.name else f"Branch_to_{node.get_leaves()[0].name[:10]}"
+                    logging.info(f"  {name}: {', '.join(parts)}")
+    return model, tree
+
+
+def calculate_model_selection_criteria(tree, counts_dict, max_chr_num, root_prior_state=None,
+                                       model_configurations=None):
+    """AR:737-812."""
+    logging.info("\n--- Model Selection based on AIC/BIC ---")
+    results = {}
+    if model_configurations is None:
+        model_configurations = [
+            {'name': 'GainLossOnly',
+             'initial_params': {'gain': 0.1, 'loss': 0.1, 'dupl': 0, 'demidupl_gain': 0,
+                                'demidupl_loss': 0, 'base_number_gain': 0, 'base_number_loss': 0,
+                                'linear_rate': 0},
+             'params_to_optimize': ['gain', 'loss']},
+            {'name': 'FullModelDefaultRates', 'initial_params': None,
+             'params_to_optimize': ChromEvolOptimizer.DEFAULT_PARAM_NAMES},
+        ]
+    for config in model_configurations:
+        name = config['name']
+        to_opt = config['params_to_optimize']
+        logging.info(f"Evaluating model: {name} with params to optimize: {to_opt}")
+        model = ChromEvolutionModel(max_chromosome_number=max_chr_num,
+                                    custom_params=config.get('initial_params'))
+        calculator = ChromEvolLikelihoodCalculator(tree, counts_dict, model)
+        n = model.max_chr + 1
+        if root_prior_state is not None and 0 <= root_prior_state <= model.max_chr:
+            root_freq = np.zeros(n)
+            root_freq[root_prior_state] = 1.0
+        else:
+            root_freq = np.ones(n) / n
+        calculator.set_root_frequencies(root_freq)
+        optimizer = ChromEvolOptimizer(tree, counts_dict, model)
+        optimizer.calculator = calculator
+        res = optimizer.optimize_parameters(params_to_optimize=to_opt, maxiter=500)
+        if res and res.success:
+            ll = -res.fun
+            k = len([p for p in to_opt if p != 'base_number'])
+            n_data = len([leaf for leaf in tree
+                          if leaf.name in counts_dict and counts_dict[leaf.name] is not None])
+            aic = 2 * k - 2 * ll
+            bic = np.log(n_data) * k - 2 * ll if n_data > 0 else aic
+            results[name] = {'log_likelihood': ll, 'AIC': aic, 'BIC': bic, 'n_params': k,
+                             'optimized_parameters': {p: v for p, v in model.params.items()
+                                                      if p in to_opt}}
+            logging.info(f"  Model {name}: LogL={ll:.2f}, AIC={aic:.2f}, BIC={bic:.2f}, N_params={k}")
+        else:
+            logging.warning(f"  Optimization failed for model: {name}")
+            results[name] = {'log_likelihood': -np.inf, 'AIC': np.inf, 'BIC': np.inf,
+                             'n_params': 0, 'optimized_parameters': {}}
+    if results:
+        try:
+            best_aic = min(results, key=lambda k: results[k]['AIC'])
+            best_bic = min(results, key=lambda k: results[k]['BIC'])
+            logging.info(f"\nBest model by AIC: {best_aic} (AIC: {results[best_aic]['AIC']:.2f})")
+            logging.info(f"Best model by BIC: {best_bic} (BIC: {results[best_bic]['BIC']:.2f})")
+        except ValueError:
+            logging.error("Could not determine best model due to invalid AIC/BIC values.")
+    return results
+
+
+def _unused():  # keep linters quiet about imports used only for their side effects
+    return torch, _lib

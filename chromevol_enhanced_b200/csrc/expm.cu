@@ -1,0 +1,654 @@
+// Batched FP64 matrix exponential for (parameter vector x branch) pairs:  P = post(expm(Q_b t_e)).
+//
+// Reference behaviour: ChromEvolutionModel.get_transition_probabilities, AR:136-166, i.e.
+// scipy.linalg.expm (Al-Mohy & Higham 2009, Algorithm 5.1: Pade order m in {3,5,7,9,13} chosen
+// from exact 1-norms, 2^s scaling + s squarings for m = 13), then max(P, 1e-12), row
+// renormalisation, NaN -> identity.
+//
+// One persistent CTA per SM; a CTA owns one matrix at a time and keeps its whole working set
+// (two n_pad x ldw FP64 matrices + staging) in shared memory when it fits (n <= 104), otherwise
+// in a per-CTA global scratch slot that lives in L2.  Per matrix:
+//   1. (m, s) from the per-vector norms scaled by t              (scalar work)
+//   2. W = sum b_{2k+1} ts^{2k} Q^{2k},  V = sum b_{2k} ts^{2k} Q^{2k}   from the shared powers
+//   3. U = W (ts Q)       -- Q has <= 9 non-zeros per column, so this is a sparse product
+//   4. solve (V - U) X = (V + U) by blocked Gauss-Jordan on [V-U | V+U]: rank-8 updates on the
+//      FP64 tensor cores (DMMA.8x8x4); pivoting inside the 8x8 diagonal tile with an
+//      element-growth monitor; optional full partial pivoting (row swaps) per panel
+//   5. X <- X^2, s times (DMMA)
+//   6. floor, renormalise, NaN check, coalesced store of P
+#include "common.cuh"
+
+namespace cevb {
+
+constexpr int NT = 512;
+constexpr int NW = NT / 32;
+constexpr int GLD = 12;      // row stride of the G staging tile (12 mod 16 -> conflict-free A frags)
+constexpr int MAXJJ = 9;     // ceil(n_pad / 32) for n_pad <= 288
+
+__constant__ double c_b3[4] = {120., 60., 12., 1.};
+__constant__ double c_b5[6] = {30240., 15120., 3360., 420., 30., 1.};
+__constant__ double c_b7[8] = {17297280., 8648640., 1995840., 277200., 25200., 1512., 56., 1.};
+__constant__ double c_b9[10] = {17643225600., 8821612800., 2075673600., 302702400., 30270240.,
+                                2162160., 110880., 3960., 90., 1.};
+__constant__ double c_b13[14] = {64764752532480000., 32382376266240000., 7771770303897600.,
+                                 1187353796428800., 129060195264000., 10559470521600.,
+                                 670442572800., 33522128640., 1323241920., 40840800., 960960.,
+                                 16380., 182., 1.};
+
+struct BranchArgs {
+    const double* pw;
+    const double* norms;
+    const uint16_t* csc;
+    const uint8_t* csc_cnt;
+    const double* t;
+    double* P;
+    int32_t* info;
+    double* scratch;
+    unsigned int* counter;
+    long long M;
+    int B, E, n, ldq, ldp, n8, npad, ldw, ldr, use_smem, full_pivot;
+    size_t scratch_doubles;  // per CTA
+};
+
+struct Order {
+    int m, s, fail;
+};
+
+// ell(ts * Q, m) of Alg. 5.1 from the per-vector scalars, in log2 space.
+__device__ int ell_scaled(const double* nr, int which, int m, double ts, int* fail) {
+    const double num = nr[CEVB_NORM_ABS7 + which];
+    if (num != num) {
+        *fail = 1;
+        return 0;
+    }
+    if (num == 0.0) return 0;  // "if not A_abs_onenorm: return 0"
+    static const double c[5] = {100800., 10059033600., 4487938430976000.,
+                                5914384781877411840000., 113250775606021113483283660800000000.};
+    const double lg = (double)(2 * m) * log2(ts) + log2(num) - log2(nr[CEVB_NORM_ONE]) -
+                      log2(c[which]) + 53.0;
+    if (lg != lg || lg == INFINITY) {  // int(ceil(inf/nan)) raises in the reference -> identity
+        *fail = 1;
+        return 0;
+    }
+    if (lg == -INFINITY) return 0;
+    const double v = ceil(lg / (double)(2 * m));
+    if (v > 1000.0) {
+        *fail = 1;
+        return 0;
+    }
+    return v > 0.0 ? (int)v : 0;
+}
+
+__device__ Order select_order(const double* nr, double t) {
+    Order o = {13, 0, 0};
+    const double d4 = t * nr[CEVB_NORM_D4], d6 = t * nr[CEVB_NORM_D6];
+    const double d8 = t * nr[CEVB_NORM_D8], d10 = t * nr[CEVB_NORM_D10];
+    const double eta1 = fmax(d4, d6);
+    if (d4 != d4 || d6 != d6 || d8 != d8 || d10 != d10) {
+        o.fail = 1;
+        return o;
+    }
+    if (eta1 < 1.495585217958292e-002 && ell_scaled(nr, 0, 3, t, &o.fail) == 0 && !o.fail) {
+        o.m = 3;
+        return o;
+    }
+    if (eta1 < 2.539398330063230e-001 && ell_scaled(nr, 1, 5, t, &o.fail) == 0 && !o.fail) {
+        o.m = 5;
+        return o;
+    }
+    const double eta3 = fmax(d6, d8);
+    if (eta3 < 9.504178996162932e-001 && ell_scaled(nr, 2, 7, t, &o.fail) == 0 && !o.fail) {
+        o.m = 7;
+        return o;
+    }
+    if (eta3 < 2.097847961257068e+000 && ell_scaled(nr, 3, 9, t, &o.fail) == 0 && !o.fail) {
+        o.m = 9;
+        return o;
+    }
+    if (o.fail) return o;
+    const double eta4 = fmax(d8, d10);
+    const double eta5 = fmin(eta3, eta4);
+    int s = 0;
+    if (eta5 != 0.0) {
+        const double v = ceil(log2(eta5 / 4.25));
+        if (v != v || v > 1000.0) {
+            o.fail = 1;
+            return o;
+        }
+        s = v > 0.0 ? (int)v : 0;
+    }
+    s += ell_scaled(nr, 4, 13, ldexp(t, -s), &o.fail);
+    o.m = 13;
+    o.s = s;
+    if (s > 1000) o.fail = 1;
+    return o;
+}
+
+// Inverse of the 8x8 diagonal tile D by Gauss-Jordan with partial pivoting inside the tile.
+// One warp; lane 4r+q holds columns 4q..4q+3 of row r of [D | I].
+__device__ void tile_inverse(const double* D, int ld, double* dinv, int lane) {
+    const int r = lane >> 2, q = lane & 3;
+    double x[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        x[j] = (q < 2) ? D[(size_t)r * ld + 4 * q + j] : ((4 * (q - 2) + j) == r ? 1.0 : 0.0);
+    unsigned used = 0u;
+    int mycol = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double myc = __shfl_sync(0xffffffffu, x[c & 3], (lane & ~3) | (c >> 2));
+        double key = ((used >> r) & 1u) ? -1.0 : ((myc != myc) ? -0.5 : fabs(myc));
+        int kr = r;
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            const double ok = __shfl_xor_sync(0xffffffffu, key, o);
+            const int orr = __shfl_xor_sync(0xffffffffu, kr, o);
+            if (ok > key || (ok == key && orr < kr)) {
+                key = ok;
+                kr = orr;
+            }
+        }
+        const int prow = kr;
+        const double pv = __shfl_sync(0xffffffffu, myc, prow << 2);
+        const double inv = 1.0 / pv;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double pr = __shfl_sync(0xffffffffu, x[j], (prow << 2) | q) * inv;
+            x[j] = (r == prow) ? pr : fma(-myc, pr, x[j]);
+        }
+        if (r == prow) mycol = c;
+        used |= 1u << prow;
+    }
+    if (q >= 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dinv[mycol * 8 + 4 * (q - 2) + j] = x[j];
+    }
+}
+
+// C(rt, ct) += G(rt) * R(:, ct) for one 8x8 tile of the augmented matrix [Aq | Bp].
+__device__ __forceinline__ void gj_update_tile(double* Aq, double* Bp, const double* rst, int ldw,
+                                               int ldr, int n8, int rt, int ct, double a0,
+                                               double a1, int g, int t, int sg, double& gmax) {
+    double* Cp = ((ct < n8) ? (Aq + ct * 8) : (Bp + (ct - n8) * 8)) + (size_t)(rt * 8 + g) * ldw;
+    double c0 = Cp[t], c1 = Cp[t + 4];
+    const double b0 = rst[t * ldr + ct * 8 + sg];
+    const double b1 = rst[(4 + t) * ldr + ct * 8 + sg];
+    dmma884(c0, c1, a0, b0);
+    dmma884(c0, c1, a1, b1);
+    Cp[t] = c0;
+    Cp[t + 4] = c1;
+    gmax = fmax(gmax, fmax(fabs(c0), fabs(c1)));
+}
+
+__device__ double block_max(double v, double* red) {
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = red[0];
+#pragma unroll
+    for (int i = 1; i < NW; ++i) r = fmax(r, red[i]);
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3, sg = sigma8(g);
+    const int n = a.n, npad = a.npad, n8 = a.n8, ldw = a.ldw, ldr = a.ldr, ldq = a.ldq;
+    const size_t matw = (size_t)npad * ldw;
+
+    double* sm = reinterpret_cast<double*>(smem_raw);
+    double *bufA, *bufB;
+    if (a.use_smem) {
+        bufA = sm;
+        bufB = sm + matw;
+        sm += 2 * matw;
+    } else {
+        bufA = a.scratch + (size_t)blockIdx.x * a.scratch_doubles;
+        bufB = bufA + matw;
+    }
+    double* gst = sm;                       // npad x GLD
+    double* rst = gst + (size_t)npad * GLD; // 8 x ldr
+    double* dinv = rst + 8 * ldr;           // 2 x 64
+    double* red = dinv + 128;               // 32
+    int* ish = reinterpret_cast<int*>(red + 32);  // [0]=work idx lo, [1]=hi, [2]=m, [3]=s, [4]=fail, [5..12]=pivots
+    // the sparse-column table of step 3 reuses the gst/rst region
+    double* tvals = gst;
+    uint16_t* trows = reinterpret_cast<uint16_t*>(tvals + (size_t)CEVB_MAX_SPARSE * n);
+    uint8_t* tcnt = reinterpret_cast<uint8_t*>(trows + (size_t)CEVB_MAX_SPARSE * n);
+
+    const size_t matq = (size_t)n * ldq;
+
+    for (;;) {
+        if (tid == 0) {
+            const unsigned long long w = atomicAdd(a.counter, 1u);
+            ish[0] = (int)(w & 0xffffffffu);
+        }
+        __syncthreads();
+        const long long idx = (long long)(unsigned)ish[0];
+        if (idx >= a.M) break;
+        const int b = (int)(idx / a.E), e = (int)(idx - (long long)b * a.E);
+        const double tb = a.t[e];
+        const double* nr = a.norms + (size_t)b * CEVB_NNORM;
+        const double* pwb = a.pw + (size_t)b * CEVB_NPOW * matq;
+        double* Pout = a.P + (size_t)idx * n * a.ldp;
+
+        if (tid == 0) {
+            Order o = {0, 0, 0};
+            if (tb > 0.0) o = select_order(nr, tb);
+            ish[2] = o.m;
+            ish[3] = o.s;
+            ish[4] = o.fail;
+        }
+        __syncthreads();
+        const int m = ish[2], s = ish[3], fail = ish[4];
+
+        if (!(tb > 0.0) || fail) {
+            // t == 0 -> identity (AR:146-148); selection failure mirrors the reference's
+            // exception path (AR:161-166), also identity.  (t < 0 / NaN never reach here.)
+            for (int i2 = tid; i2 < n * a.ldp; i2 += NT) {
+                const int i = i2 / a.ldp, j = i2 - i * a.ldp;
+                Pout[i2] = (i == j) ? 1.0 : 0.0;
+            }
+            if (tid == 0)
+                a.info[idx] = fail ? (13 | (CEVB_INFO_NAN_FALLBACK << 16))
+                                   : (CEVB_INFO_IDENTITY_T0 << 16);
+            __syncthreads();
+            continue;
+        }
+
+        const double ts = ldexp(tb, -s);
+        const int kmax = (m == 13) ? 6 : (m >> 1);
+        const double* bc = (m == 3) ? c_b3 : (m == 5) ? c_b5 : (m == 7) ? c_b7 : (m == 9) ? c_b9 : c_b13;
+
+        // ---- 2. W -> bufA, V -> bufB ------------------------------------------------------
+        {
+            double cw[7], cv[7];
+            double pk = 1.0;
+            const double ts2 = ts * ts;
+#pragma unroll
+            for (int k = 1; k <= 6; ++k) {
+                pk *= ts2;
+                cw[k] = (k <= kmax) ? bc[2 * k + 1] * pk : 0.0;
+                cv[k] = (k <= kmax) ? bc[2 * k] * pk : 0.0;
+            }
+            const double b1 = bc[1], b0 = bc[0];
+            for (int i2 = tid; i2 < npad * npad; i2 += NT) {
+                const int i = i2 / npad, j = i2 - i * npad;
+                double w = 0.0, v = 0.0;
+                if (i < n && j < n) {
+                    const double* src = pwb + (size_t)i * ldq + j;
+#pragma unroll
+                    for (int k = 6; k >= 1; --k) {
+                        if (k <= kmax) {
+                            const double x = src[(size_t)k * matq];
+                            w = fma(cw[k], x, w);
+                            v = fma(cv[k], x, v);
+                        }
+                    }
+                }
+                if (i == j) {
+                    w += b1;
+                    v += b0;
+                }
+                bufA[(size_t)i * ldw + j] = w;
+                bufB[(size_t)i * ldw + j] = v;
+            }
+        }
+        // stage the sparse structure of A = ts * Q (values pre-scaled)
+        const bool dense = nr[CEVB_NORM_DENSE] != 0.0;
+        if (!dense) {
+            for (int j = tid; j < n; j += NT) tcnt[j] = a.csc_cnt[(size_t)b * n + j];
+            for (int i2 = tid; i2 < CEVB_MAX_SPARSE * n; i2 += NT) {
+                const int c = i2 / n, j = i2 - c * n;
+                const int cnt = a.csc_cnt[(size_t)b * n + j];
+                uint16_t r = 0;
+                double v = 0.0;
+                if (c < cnt) {
+                    r = a.csc[((size_t)b * CEVB_MAX_SPARSE + c) * n + j];
+                    v = ts * pwb[(size_t)r * ldq + j];
+                }
+                trows[i2] = r;
+                tvals[i2] = v;
+            }
+        }
+        __syncthreads();
+
+        // ---- 3. U = W * (ts Q), in place in bufA, one warp per row -------------------------
+        for (int i = warp; i < npad; i += NW) {
+            double* wrow = bufA + (size_t)i * ldw;
+            double out[MAXJJ];
+#pragma unroll
+            for (int jj = 0; jj < MAXJJ; ++jj) {
+                const int j = lane + 32 * jj;
+                double acc = 0.0;
+                if (i < n && j < n) {
+                    if (!dense) {
+                        const int cnt = tcnt[j];
+                        for (int c = 0; c < cnt; ++c)
+                            acc = fma(wrow[trows[c * n + j]], tvals[c * n + j], acc);
+                    } else {
+                        for (int k = 0; k < n; ++k)
+                            acc = fma(wrow[k], ts * pwb[(size_t)k * ldq + j], acc);
+                    }
+                }
+                out[jj] = acc;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int jj = 0; jj < MAXJJ; ++jj) {
+                const int j = lane + 32 * jj;
+                if (j < npad) wrow[j] = out[jj];
+            }
+        }
+        __syncthreads();
+
+        // ---- 4. Aq = V - U (bufA), Bp = V + U (bufB) --------------------------------------
+        double* Aq = bufA;
+        double* Bp = bufB;
+        double gmax0 = 0.0;
+        for (int i2 = tid; i2 < npad * npad; i2 += NT) {
+            const int i = i2 / npad, j = i2 - i * npad;
+            const size_t o = (size_t)i * ldw + j;
+            const double u = Aq[o], v = Bp[o];
+            const double qm = v - u, pm = v + u;
+            Aq[o] = qm;
+            Bp[o] = pm;
+            gmax0 = fmax(gmax0, fmax(fabs(qm), fabs(pm)));
+        }
+        __syncthreads();
+
+        // ---- 5. blocked Gauss-Jordan ------------------------------------------------------
+        double gmax = 0.0;
+        if (!a.full_pivot) {
+            if (warp == 0) tile_inverse(Aq, ldw, dinv, lane);
+            __syncthreads();
+        }
+        for (int kt = 0; kt < n8; ++kt) {
+            const int k0 = kt * 8;
+            double* dcur = dinv + (kt & 1) * 64;
+            if (a.full_pivot) {
+                // choose the 8 pivot rows of this panel by partial pivoting over all rows >= k0
+                // (LU on a copy of the panel), swap them into the diagonal tile, then invert it.
+                dcur = dinv;
+                for (int i2 = tid; i2 < (npad - k0) * 8; i2 += NT) {
+                    const int i = k0 + (i2 >> 3), c = i2 & 7;
+                    gst[i * GLD + c] = Aq[(size_t)i * ldw + k0 + c];
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    for (int c = 0; c < 8; ++c) {
+                        double best = -1.0;
+                        int bi = k0 + c;
+                        for (int i = k0 + c + lane; i < npad; i += 32) {
+                            const double v = fabs(gst[i * GLD + c]);
+                            if (v > best) {
+                                best = v;
+                                bi = i;
+                            }
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            if (ob > best || (ob == best && oi < bi)) {
+                                best = ob;
+                                bi = oi;
+                            }
+                        }
+                        if (lane == 0) ish[5 + c] = bi;
+                        if (bi != k0 + c && lane < 8) {
+                            const double tmp = gst[bi * GLD + lane];
+                            gst[bi * GLD + lane] = gst[(k0 + c) * GLD + lane];
+                            gst[(k0 + c) * GLD + lane] = tmp;
+                        }
+                        __syncwarp();
+                        const double pv = gst[(k0 + c) * GLD + c];
+                        for (int i = k0 + c + 1 + lane; i < npad; i += 32) {
+                            const double l = gst[i * GLD + c] / pv;
+                            for (int c2 = c + 1; c2 < 8; ++c2)
+                                gst[i * GLD + c2] = fma(-l, gst[(k0 + c) * GLD + c2], gst[i * GLD + c2]);
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
+                for (int c = 0; c < 8; ++c) {
+                    const int p = ish[5 + c];
+                    if (p != k0 + c) {
+                        for (int cc = k0 + tid; cc < 2 * npad; cc += NT) {
+                            double* r1 = (cc < npad) ? (Aq + cc) : (Bp + (cc - npad));
+                            const double tmp = r1[(size_t)p * ldw];
+                            r1[(size_t)p * ldw] = r1[(size_t)(k0 + c) * ldw];
+                            r1[(size_t)(k0 + c) * ldw] = tmp;
+                        }
+                    }
+                    __syncthreads();
+                }
+                if (warp == 0) tile_inverse(Aq + (size_t)k0 * ldw + k0, ldw, dcur, lane);
+                __syncthreads();
+            }
+            // G = -(column panel) * Dinv, with (Dinv - I) in the pivot rows; R = pivot rows
+            for (int i2 = tid; i2 < npad * 8; i2 += NT) {
+                const int i = i2 >> 3, c = i2 & 7;
+                double gv;
+                if (i >= k0 && i < k0 + 8) {
+                    gv = dcur[(i - k0) * 8 + c] - ((i - k0) == c ? 1.0 : 0.0);
+                } else {
+                    const double* ar = Aq + (size_t)i * ldw + k0;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc = fma(ar[j], dcur[j * 8 + c], acc);
+                    gv = -acc;
+                }
+                gst[i * GLD + c] = gv;
+            }
+            {
+                const int c_lo = k0 + 8, wcols = 2 * npad - c_lo;
+                for (int i2 = tid; i2 < 8 * wcols; i2 += NT) {
+                    const int r = i2 / wcols, cc = c_lo + (i2 - r * wcols);
+                    rst[r * ldr + cc] = (cc < npad) ? Aq[(size_t)(k0 + r) * ldw + cc]
+                                                    : Bp[(size_t)(k0 + r) * ldw + cc - npad];
+                }
+            }
+            __syncthreads();
+
+            // trailing update: tiles (rt, ct), ct in (kt, 2*n8)
+            const int ct_lo = kt + 1;
+            const bool lookahead = (!a.full_pivot) && (kt + 1 < n8);
+            if (warp == 0 && lookahead) {
+                const int rt = kt + 1;
+                const double a0 = gst[(rt * 8 + g) * GLD + t4], a1 = gst[(rt * 8 + g) * GLD + 4 + t4];
+                gj_update_tile(Aq, Bp, rst, ldw, ldr, n8, rt, kt + 1, a0, a1, g, t4, sg, gmax);
+                __syncwarp();
+                tile_inverse(Aq + (size_t)(k0 + 8) * ldw + k0 + 8, ldw, dinv + ((kt + 1) & 1) * 64, lane);
+            }
+            {
+                const int nct = 2 * n8 - ct_lo;
+                const int nch = (nct + 3) >> 2;
+                const int ntask = n8 * nch;
+                const int w0 = lookahead ? 1 : 0;  // warp 0 is busy with the next diagonal tile
+                if (warp >= w0) {
+                    for (int task = warp - w0; task < ntask; task += NW - w0) {
+                        const int rt = task % n8, ch = task / n8;
+                        const double a0 = gst[(rt * 8 + g) * GLD + t4];
+                        const double a1 = gst[(rt * 8 + g) * GLD + 4 + t4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int ct = ct_lo + ch * 4 + q;
+                            if (ct < 2 * n8 && !(lookahead && rt == kt + 1 && ct == kt + 1))
+                                gj_update_tile(Aq, Bp, rst, ldw, ldr, n8, rt, ct, a0, a1, g, t4, sg, gmax);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- 6. squarings -----------------------------------------------------------------
+        double* src = Bp;
+        double* dst = Aq;
+        for (int it = 0; it < s; ++it) {
+            const int nch = (n8 + 3) >> 2;
+            const int ntask = n8 * nch;
+            for (int task = warp; task < ntask; task += NW) {
+                const int rt = task % n8, ch = task / n8;
+                const int ct0 = ch * 4;
+                double acc[4][2] = {};
+                const double* arow = src + (size_t)(rt * 8 + g) * ldw + t4;
+                const double* bcol = src + (size_t)t4 * ldw + ct0 * 8 + sg;
+                for (int k4 = 0; k4 < npad; k4 += 4) {
+                    const double av = arow[k4];
+                    const double* bp = bcol + (size_t)k4 * ldw;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (ct0 + q < n8) dmma884(acc[q][0], acc[q][1], av, bp[q * 8]);
+                    }
+                }
+                double* drow = dst + (size_t)(rt * 8 + g) * ldw + ct0 * 8 + t4;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (ct0 + q < n8) {
+                        drow[q * 8] = acc[q][0];
+                        drow[q * 8 + 4] = acc[q][1];
+                    }
+                }
+            }
+            __syncthreads();
+            double* tmp = src;
+            src = dst;
+            dst = tmp;
+        }
+
+        // ---- 7. floor, renormalise, NaN check, store (AR:153-159) --------------------------
+        int nanflag = 0;
+        for (int i = warp; i < n; i += NW) {
+            const double* xr = src + (size_t)i * ldw;
+            double p[MAXJJ];
+            double rs = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < MAXJJ; ++jj) {
+                const int j = lane + 32 * jj;
+                double v = 0.0;
+                if (j < n) {
+                    const double x = xr[j];
+                    v = (x != x) ? x : fmax(x, 1e-12);
+                }
+                p[jj] = v;
+                rs += v;
+            }
+            rs = warp_sum(rs);
+#pragma unroll
+            for (int jj = 0; jj < MAXJJ; ++jj) {
+                const int j = lane + 32 * jj;
+                if (j < n) {
+                    const double o = p[jj] / rs;
+                    if (o != o) nanflag = 1;
+                    Pout[(size_t)i * a.ldp + j] = o;
+                } else if (j < a.ldp) {
+                    Pout[(size_t)i * a.ldp + j] = 0.0;
+                }
+            }
+        }
+        nanflag = __syncthreads_or(nanflag);
+        if (nanflag) {
+            for (int i2 = tid; i2 < n * a.ldp; i2 += NT) {
+                const int i = i2 / a.ldp, j = i2 - i * a.ldp;
+                Pout[i2] = (i == j) ? 1.0 : 0.0;
+            }
+        }
+        const double g0 = block_max(gmax0, red);
+        const double g1 = block_max(gmax, red);
+        if (tid == 0) {
+            int flags = nanflag ? CEVB_INFO_NAN_FALLBACK : 0;
+            if (g1 > 1.0e3 * g0 && g1 < INFINITY) flags |= CEVB_INFO_GROWTH;
+            if (a.full_pivot) flags |= CEVB_INFO_REPIVOTED;
+            a.info[idx] = m | (s << 8) | (flags << 16);
+        }
+        __syncthreads();
+    }
+}
+
+static size_t branch_smem_bytes(int n, bool with_matrices) {
+    const int n8 = (n + 7) / 8, npad = n8 * 8, ldw = npad + 4, ldr = 2 * npad + 4;
+    size_t d = (size_t)npad * GLD + 8 * (size_t)ldr + 128 + 32;
+    // the sparse table (values + u16 rows + u8 counts) must fit in the gst+rst region
+    const size_t tab = (size_t)CEVB_MAX_SPARSE * n * 10 + n + 16;
+    size_t stage = ((size_t)npad * GLD + 8 * (size_t)ldr) * 8;
+    if (tab > stage) d += (tab - stage + 7) / 8;
+    if (with_matrices) d += 2 * (size_t)npad * ldw;
+    return d * 8 + 64;
+}
+
+static int g_sm_count = 0;
+static size_t g_smem_optin = 0;
+
+static int query_device() {
+    if (g_sm_count) return 0;
+    int dev = 0;
+    CEVB_CHECK_CUDA(cudaGetDevice(&dev));
+    int sm = 0, optin = 0;
+    CEVB_CHECK_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+    CEVB_CHECK_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    g_sm_count = sm;
+    g_smem_optin = (size_t)optin;
+    return 0;
+}
+
+}  // namespace cevb
+
+using namespace cevb;
+
+extern "C" size_t cevb_expm_scratch_bytes(int n) {
+    if (query_device() != 0) return 0;
+    if (branch_smem_bytes(n, true) <= g_smem_optin) return 0;
+    const int n8 = (n + 7) / 8, npad = n8 * 8, ldw = npad + 4;
+    return 2 * (size_t)npad * ldw * sizeof(double);
+}
+
+extern "C" int cevb_expm_grid(int n, long long n_matrices) {
+    if (query_device() != 0) return 0;
+    const bool in_smem = branch_smem_bytes(n, true) <= g_smem_optin;
+    long long ctas = (long long)g_sm_count * (in_smem ? 1 : 2);
+    if (n_matrices < ctas) ctas = n_matrices;
+    return (int)(ctas < 1 ? 1 : ctas);
+}
+
+extern "C" int cevb_expm_branches(const double* pw, const double* norms, const uint16_t* csc,
+                                  const uint8_t* csc_cnt, const double* t, int B, int E, int n,
+                                  double* P, int32_t* info, void* scratch, unsigned int* counter,
+                                  int full_pivot, void* stream) {
+    if (B <= 0 || E <= 0) return 0;
+    if (n < 2 || n > 288) {
+        set_error("cevb_expm_branches: n=%d outside the supported range 2..288", n);
+        return -1;
+    }
+    if (query_device() != 0) return -2;
+    cudaStream_t st = (cudaStream_t)stream;
+    BranchArgs a;
+    a.pw = pw; a.norms = norms; a.csc = csc; a.csc_cnt = csc_cnt; a.t = t; a.P = P; a.info = info;
+    a.scratch = (double*)scratch; a.counter = counter;
+    a.M = (long long)B * E; a.B = B; a.E = E; a.n = n;
+    a.ldq = ldq_of(n); a.ldp = ldp_of(n);
+    a.n8 = (n + 7) / 8; a.npad = a.n8 * 8; a.ldw = a.npad + 4; a.ldr = 2 * a.npad + 4;
+    a.full_pivot = full_pivot ? 1 : 0;
+    a.use_smem = branch_smem_bytes(n, true) <= g_smem_optin ? 1 : 0;
+    a.scratch_doubles = 2 * (size_t)a.npad * a.ldw;
+    if (!a.use_smem && scratch == nullptr) {
+        set_error("cevb_expm_branches: n=%d needs a global scratch buffer", n);
+        return -1;
+    }
+    const size_t smem = branch_smem_bytes(n, a.use_smem != 0);
+    if (smem > g_smem_optin) {
+        set_error("cevb_expm_branches: staging for n=%d needs %zu B of shared memory", n, smem);
+        return -1;
+    }
+    CEVB_CHECK_CUDA(cudaFuncSetAttribute(expm_branch_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CEVB_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    const int grid = cevb_expm_grid(n, a.M);
+    expm_branch_kernel<<<grid, NT, smem, st>>>(a);
+    CEVB_CHECK_LAUNCH("expm_branch_kernel");
+    return 0;
+}

@@ -1,0 +1,256 @@
+"""Batched device engine: parameter vectors -> tree log-likelihoods on one B200.
+
+This is the additive, batched entry point that sits beside the reference-shaped classes in
+``ancestral_reconstruction.py``.  Buffers are torch CUDA tensors (device
+memory and streams only); all arithmetic happens in the hand-written kernels behind the C ABI.
+
+Pipeline per chunk of parameter vectors (one stream, no host synchronisation inside):
+    cevb_build_q -> cevb_expm_prepare -> cevb_expm_branches -> cevb_prune [-> cevb_argmax_states]
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .flatten import FlatTree
+
+PARAM_ORDER = ['gain', 'loss', 'dupl', 'demidupl_gain', 'demidupl_loss',
+               'base_number_gain', 'base_number_loss', 'linear_rate', 'base_number']
+
+INFO_IDENTITY_T0 = 1
+INFO_NAN_FALLBACK = 2
+INFO_GROWTH = 4
+INFO_REPIVOTED = 8
+
+
+def params_to_row(params):
+    """dict (reference layout, AR:38-48) -> 9 doubles in the device order."""
+    row = np.zeros(9, dtype=np.float64)
+    for k, name in enumerate(PARAM_ORDER[:8]):
+        v = params.get(name, 0)
+        row[k] = float(v) if v is not None else 0.0
+    bn = params.get('base_number')
+    row[8] = float(bn) if (bn is not None and bn > 0) else 0.0
+    return row
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class ExpmWorkspace:
+    """Device buffers for `cap` parameter vectors x `n_t` branch lengths of order n."""
+
+    def __init__(self, n, n_t, cap, device):
+        lib = _lib.load()
+        self.n, self.n_t, self.cap, self.device = n, n_t, cap, device
+        self.ldq = lib.cevb_ldq(n)
+        self.ldp = lib.cevb_ldp(n)
+        f64 = dict(dtype=torch.float64, device=device)
+        self.params = torch.zeros((cap, 9), **f64)
+        self.pw = torch.zeros((cap, 7, n, self.ldq), **f64)
+        self.norms = torch.zeros((cap, 16), **f64)
+        self.csc = torch.zeros((cap, 12, n), dtype=torch.int16, device=device)
+        self.csc_cnt = torch.zeros((cap, n), dtype=torch.uint8, device=device)
+        self.P = torch.empty((cap, n_t, n, self.ldp), **f64)
+        self.info = torch.zeros((cap, n_t), dtype=torch.int32, device=device)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        scratch_bytes = lib.cevb_expm_scratch_bytes(n)
+        grid = lib.cevb_expm_grid(n, cap * n_t)
+        self.scratch = (torch.empty(scratch_bytes * grid // 8 + 8, **f64)
+                        if scratch_bytes else None)
+
+    @staticmethod
+    def bytes_per_vector(n, n_t):
+        ld = n + (n & 1)
+        return 8 * (7 * n * ld + n_t * n * ld) + 4 * n_t + 64 * n
+
+
+class LikelihoodEngine:
+    """Tree + data resident on the device; evaluates batches of parameter vectors."""
+
+    def __init__(self, flat: FlatTree, device=None, max_workspace_bytes=32 << 30, chunk=None):
+        _lib.require_device()
+        self.lib = _lib.load()
+        self.flat = flat
+        self.device = torch.device(device if device is not None else
+                                   f"cuda:{torch.cuda.current_device()}")
+        self.n = flat.n_states
+        self.ldp = self.lib.cevb_ldp(self.n)
+        i32 = dict(dtype=torch.int32, device=self.device)
+        self.d_level_nodes = torch.as_tensor(flat.level_nodes, **i32)
+        self.d_child_off = torch.as_tensor(flat.child_off, **i32)
+        self.d_child_idx = torch.as_tensor(flat.child_idx, **i32)
+        self.d_branch_of = torch.as_tensor(flat.branch_of, **i32)
+        self.d_leaf_code = torch.as_tensor(flat.leaf_code, **i32)
+        self.d_t = torch.as_tensor(flat.t_unique, dtype=torch.float64, device=self.device)
+        self.h_level_off = np.ascontiguousarray(flat.level_off, dtype=np.int32)
+        per_vec = (ExpmWorkspace.bytes_per_vector(self.n, flat.n_t)
+                   + 8 * flat.n_nodes * self.ldp)
+        if chunk is None:
+            chunk = max(1, min(4096, int(max_workspace_bytes // max(per_vec, 1))))
+        self.chunk = int(chunk)
+        self._ws = None
+        self._node_vec = None
+        self._cap = 0
+        self.last_info = None
+        self.repivot_events = 0
+
+    # ------------------------------------------------------------------ buffers
+    def _ensure(self, cap):
+        if self._ws is not None and self._cap >= cap:
+            return
+        self._ws = None
+        self._node_vec = None
+        self._ws = ExpmWorkspace(self.n, self.flat.n_t, cap, self.device)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self._node_vec = torch.empty((cap, self.flat.n_nodes, self.ldp), **f64)
+        self._logl = torch.empty(cap, **f64)
+        self._rescales = torch.zeros(cap, dtype=torch.int32, device=self.device)
+        self._cap = cap
+
+    def root_freq_tensor(self, root_freq):
+        if root_freq is None:
+            root_freq = np.ones(self.n) / self.n
+        return torch.as_tensor(np.ascontiguousarray(root_freq, dtype=np.float64),
+                               device=self.device)
+
+    # ------------------------------------------------------------------ stages (async)
+    def _transition_matrices(self, ws, nb, full_pivot=0):
+        lib, st = self.lib, _stream_ptr()
+        _lib.check(lib.cevb_build_q(_lib.ptr(ws.params), nb, self.n, _lib.ptr(ws.pw), st),
+                   "cevb_build_q")
+        _lib.check(lib.cevb_expm_prepare(_lib.ptr(ws.pw), nb, self.n, _lib.ptr(ws.norms),
+                                         _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt), st),
+                   "cevb_expm_prepare")
+        _lib.check(lib.cevb_expm_branches(_lib.ptr(ws.pw), _lib.ptr(ws.norms), _lib.ptr(ws.csc),
+                                          _lib.ptr(ws.csc_cnt), _lib.ptr(self.d_t), nb,
+                                          self.flat.n_t, self.n, _lib.ptr(ws.P), _lib.ptr(ws.info),
+                                          _lib.ptr(ws.scratch), _lib.ptr(ws.counter), full_pivot,
+                                          st), "cevb_expm_branches")
+
+    def _prune(self, ws, nb, d_root_freq):
+        f = self.flat
+        _lib.check(self.lib.cevb_prune(
+            _lib.ptr(ws.P), nb, f.n_t, self.n, f.n_nodes, f.root, _lib.ptr(self.d_level_nodes),
+            self.h_level_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), f.n_levels,
+            _lib.ptr(self.d_child_off), _lib.ptr(self.d_child_idx), _lib.ptr(self.d_branch_of),
+            _lib.ptr(self.d_leaf_code), _lib.ptr(d_root_freq), _lib.ptr(self._node_vec),
+            _lib.ptr(self._logl), _lib.ptr(self._rescales), _stream_ptr()), "cevb_prune")
+
+    def _run_chunk(self, d_params_chunk, d_root_freq, check_growth=True):
+        nb = d_params_chunk.shape[0]
+        ws = self._ws
+        ws.params[:nb].copy_(d_params_chunk)
+        self._transition_matrices(ws, nb, 0)
+        if check_growth:
+            flagged = bool(((ws.info[:nb] >> 16) & INFO_GROWTH).any().item())
+            if flagged:  # rare: redo the chunk with full partial pivoting
+                self.repivot_events += 1
+                self._transition_matrices(ws, nb, 1)
+        self._prune(ws, nb, d_root_freq)
+
+    # ------------------------------------------------------------------ public
+    def log_likelihood(self, params, root_freq=None, check_growth=True):
+        """params: (B, 9) array-like or CUDA tensor in PARAM_ORDER -> CUDA tensor (B,) of logL."""
+        if torch.is_tensor(params):
+            d_params = params.to(device=self.device, dtype=torch.float64)
+        else:
+            d_params = torch.as_tensor(np.ascontiguousarray(params, dtype=np.float64),
+                                       device=self.device)
+        if d_params.dim() == 1:
+            d_params = d_params[None, :]
+        B = d_params.shape[0]
+        d_root = root_freq if torch.is_tensor(root_freq) else self.root_freq_tensor(root_freq)
+        out = torch.empty(B, dtype=torch.float64, device=self.device)
+        self.rescale_counts = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self._ensure(min(self.chunk, B))
+        for lo in range(0, B, self._cap):
+            hi = min(B, lo + self._cap)
+            self._run_chunk(d_params[lo:hi], d_root, check_growth)
+            out[lo:hi].copy_(self._logl[:hi - lo])
+            self.rescale_counts[lo:hi].copy_(self._rescales[:hi - lo])
+        self.last_batch = B
+        return out
+
+    def node_vectors(self, which=0):
+        """Conditional-likelihood vectors (n_nodes, n) of vector `which` of the last chunk."""
+        return self._node_vec[which, :, :self.n]
+
+    def transition_matrices(self, which=0):
+        """(n_t, n, n) view of the P matrices of vector `which` of the last chunk."""
+        return self._ws.P[which, :, :, :self.n]
+
+    def order_info(self, which=0):
+        info = self._ws.info[which].cpu().numpy()
+        return info & 0xff, (info >> 8) & 0xff, info >> 16
+
+    def ancestral_states(self, which=0, want_probs=True):
+        """argmax states for vector `which` of the last chunk -> (ml_count, ml_prob, probs)."""
+        f = self.flat
+        vec = self._node_vec[which:which + 1]
+        ml_count = torch.empty(f.n_nodes, dtype=torch.int32, device=self.device)
+        ml_prob = torch.empty(f.n_nodes, dtype=torch.float64, device=self.device)
+        probs = (torch.zeros((f.n_nodes, self.ldp), dtype=torch.float64, device=self.device)
+                 if want_probs else None)
+        _lib.check(self.lib.cevb_argmax_states(_lib.ptr(vec), 1, f.n_nodes, self.n,
+                                               _lib.ptr(ml_count), _lib.ptr(ml_prob),
+                                               _lib.ptr(probs), _stream_ptr()),
+                   "cevb_argmax_states")
+        return ml_count, ml_prob, (probs[:, :self.n] if want_probs else None)
+
+
+# ---------------------------------------------------------------------- single-matrix helpers
+def rate_matrix(params_row, n, device=None):
+    """One Q (n x n, host ndarray) from the device kernel -- AR:75-134."""
+    _lib.require_device()
+    lib = _lib.load()
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    rows = np.atleast_2d(np.asarray(params_row, dtype=np.float64))
+    B = rows.shape[0]
+    ldq = lib.cevb_ldq(n)
+    d_params = torch.as_tensor(rows, device=device)
+    pw = torch.zeros((B, 7, n, ldq), dtype=torch.float64, device=device)
+    _lib.check(lib.cevb_build_q(_lib.ptr(d_params), B, n, _lib.ptr(pw), _stream_ptr()),
+               "cevb_build_q")
+    return pw[:, 0, :, :n].cpu().numpy()
+
+
+def transition_matrices(params_rows, times, n, device=None, full_pivot=0, return_info=False,
+                        q_matrices=None):
+    """P[b, e] = post(expm(Q_b t_e)) as a host ndarray (B, E, n, n) -- AR:136-166.
+
+    ``q_matrices`` (B, n, n), when given, replaces the rate matrices built from ``params_rows``
+    (any real square matrices: the expm kernels do not assume ChromEvol structure)."""
+    _lib.require_device()
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    times = np.atleast_1d(np.asarray(times, dtype=np.float64))
+    if q_matrices is not None:
+        q_matrices = np.asarray(q_matrices, dtype=np.float64).reshape(-1, n, n)
+        rows = np.zeros((q_matrices.shape[0], 9))
+    else:
+        rows = np.atleast_2d(np.asarray(params_rows, dtype=np.float64))
+    B, E = rows.shape[0], times.shape[0]
+    ws = ExpmWorkspace(n, E, B, device)
+    ws.params.copy_(torch.as_tensor(rows, device=device))
+    d_t = torch.as_tensor(times, device=device)
+    lib, st = _lib.load(), _stream_ptr()
+    if q_matrices is not None:
+        ws.pw[:, 0, :, :n].copy_(torch.as_tensor(q_matrices, device=device))
+    else:
+        _lib.check(lib.cevb_build_q(_lib.ptr(ws.params), B, n, _lib.ptr(ws.pw), st),
+                   "cevb_build_q")
+    _lib.check(lib.cevb_expm_prepare(_lib.ptr(ws.pw), B, n, _lib.ptr(ws.norms), _lib.ptr(ws.csc),
+                                     _lib.ptr(ws.csc_cnt), st), "cevb_expm_prepare")
+    _lib.check(lib.cevb_expm_branches(_lib.ptr(ws.pw), _lib.ptr(ws.norms), _lib.ptr(ws.csc),
+                                      _lib.ptr(ws.csc_cnt), _lib.ptr(d_t), B, E, n, _lib.ptr(ws.P),
+                                      _lib.ptr(ws.info), _lib.ptr(ws.scratch),
+                                      _lib.ptr(ws.counter), full_pivot, st), "cevb_expm_branches")
+    P = ws.P[:, :, :, :n].cpu().numpy()
+    if return_info:
+        info = ws.info.cpu().numpy()
+        return P, info & 0xff, (info >> 8) & 0xff, info >> 16
+    return P

@@ -1,0 +1,143 @@
+/*
+ * chromevol_b200.h -- C ABI of the B200 (sm_100a) chromosome-number likelihood path.
+ *
+ * The reference (Biols9527/ChromEvol-Enhanced) is a single pure-Python file,
+ * src/ancestral_reconstruction.py ("AR" below); it has no FFI of its own.  The entry points
+ * here are what a ctypes binding for its hot path binds: each one
+ * replaces the numpy/scipy body of one reference method and is called by the Python classes
+ * in chromevol_enhanced_b200/ that keep the reference's signatures.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (torch.Tensor.data_ptr()) unless marked "host";
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); calls are asynchronous
+ *     on that stream unless stated otherwise;
+ *   - return value: 0 = ok, negative = error (see cevb_last_error); nothing throws;
+ *   - all floating point is IEEE binary64; matrices are row-major;
+ *   - n = max_chromosome_number + 1 states (0..N), the reference's matrix order (AR:84).
+ *
+ * Layouts
+ *   params  [B][9]            gain, loss, dupl, demidupl_gain, demidupl_loss,
+ *                             base_number_gain, base_number_loss, linear_rate  (AR:22 order)
+ *                             then base_number as a double (0 = None)          (AR:44)
+ *   pw      [B][7][n][ldq]    slot 0 = Q, slot k = Q^(2k), k = 1..6; ldq = cevb_ldq(n)
+ *   norms   [B][16]           see CEVB_NORM_* below
+ *   csc     [B][CEVB_MAX_SPARSE][n] uint16 row indices of the non-zeros of each Q column,
+ *   csc_cnt [B][n]            uint8 count per column (255 = column too dense)
+ *   t       [E]               branch lengths (>= 0; host applies AR:143-145 / AR:224-227)
+ *   P       [B][E][n][ldp]    post-processed transition matrices, ldp = cevb_ldp(n)
+ *   info    [B][E]            int32: Pade order m | s << 8 | flags << 16 (CEVB_INFO_*)
+ */
+#ifndef CHROMEVOL_B200_H
+#define CHROMEVOL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CEVB_ABI_VERSION 1
+#define CEVB_NPARAM 9
+#define CEVB_NPOW 7
+#define CEVB_NNORM 16
+#define CEVB_MAX_SPARSE 12
+#define CEVB_NEVENT 8
+
+/* norms[b][.] */
+#define CEVB_NORM_ONE 0      /* ||Q||_1 */
+#define CEVB_NORM_D4 1       /* ||Q^4||_1^(1/4)   */
+#define CEVB_NORM_D6 2
+#define CEVB_NORM_D8 3
+#define CEVB_NORM_D10 4
+#define CEVB_NORM_ABS7 5     /* || |Q|^7 ||_1, then ^11, ^15, ^19, ^27 */
+#define CEVB_NORM_DENSE 10   /* 1.0 if some column of Q has more than CEVB_MAX_SPARSE non-zeros */
+
+/* info flags (bits 16..) */
+#define CEVB_INFO_IDENTITY_T0 1   /* t == 0 -> exact identity (AR:146-148)            */
+#define CEVB_INFO_NAN_FALLBACK 2  /* NaN after renormalisation -> identity (AR:156-159) */
+#define CEVB_INFO_GROWTH 4        /* element growth monitor tripped in the tile-pivoted solve */
+#define CEVB_INFO_REPIVOTED 8     /* matrix was redone with full partial pivoting      */
+
+/* ---- probes -------------------------------------------------------------------------- */
+int cevb_abi_version(void);
+/* host out-params; returns 0 when a CUDA device with compute capability 10.x is current */
+int cevb_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin);
+const char* cevb_last_error(void);
+int cevb_ldq(int n);   /* row stride (doubles) of Q / power matrices          */
+int cevb_ldp(int n);   /* row stride (doubles) of P and of node vectors       */
+/* bytes of per-CTA global scratch cevb_expm_branches needs (0 when the working set fits in
+ * shared memory), and how many CTAs it launches */
+size_t cevb_expm_scratch_bytes(int n);
+int cevb_expm_grid(int n, long long n_matrices);
+
+/* ---- (1) rate matrix: replaces ChromEvolutionModel.build_transition_rate_matrix, AR:75-134.
+ * Writes slot 0 of pw for every parameter vector, bit-identical to the reference's Q. */
+int cevb_build_q(const double* params, int B, int n, double* pw, void* stream);
+
+/* ---- (2a) per-parameter-vector tables for expm: even powers Q^2..Q^12 (DMMA GEMMs), the
+ * 1-norms Algorithm 5.1 of Al-Mohy & Higham 2009 needs (what scipy.linalg.expm, AR:151,
+ * evaluates per call), and the sparse column structure of Q. */
+int cevb_expm_prepare(double* pw, int B, int n, double* norms, uint16_t* csc, uint8_t* csc_cnt,
+                      void* stream);
+
+/* ---- (2b) transition matrices: replaces ChromEvolutionModel.get_transition_probabilities,
+ * AR:136-166, for every (parameter vector, branch) pair: P = expm(Q t) by variable-order
+ * Pade + scaling and squaring, floor 1e-12, row renormalisation, NaN -> identity, t == 0 ->
+ * identity.  `scratch` must hold cevb_expm_grid() * cevb_expm_scratch_bytes() bytes (may be
+ * NULL when that is 0).  `counter` is one zero-initialised uint32 used as a work queue head. */
+int cevb_expm_branches(const double* pw, const double* norms, const uint16_t* csc,
+                       const uint8_t* csc_cnt, const double* t, int B, int E, int n, double* P,
+                       int32_t* info, void* scratch, unsigned int* counter, int full_pivot,
+                       void* stream);
+
+/* ---- (3) Felsenstein pruning: replaces ChromEvolLikelihoodCalculator.
+ * calculate_likelihood_at_node / calculate_total_log_likelihood, AR:189-272.
+ * Tree arrays (int32, device): nodes are numbered 0..n_nodes-1;
+ *   level_nodes [n_internal]       internal nodes grouped by level (children before parents),
+ *   level_off   [n_levels+1] HOST  offsets into level_nodes,
+ *   child_off   [n_nodes+1]        CSR offsets into child_idx (file order, AR:221),
+ *   child_idx   [n_branches]       child node of every branch,
+ *   branch_of   [n_nodes]          index into the E axis of P for the branch above a node,
+ *   leaf_code   [n_nodes]          >= 0 observed state (already clamped, AR:204-208),
+ *                                  -1 missing data (uniform, AR:209-211), -2 internal node.
+ * node_vec [B][n_nodes][ldp] receives every conditional-likelihood vector, logl [B] the tree
+ * log-likelihood (-inf when L <= 0), rescales [B] how many times the AR:242 rescale fired. */
+int cevb_prune(const double* P, int B, int E, int n, int n_nodes, int root,
+               const int32_t* level_nodes, const int32_t* level_off_host, int n_levels,
+               const int32_t* child_off, const int32_t* child_idx, const int32_t* branch_of,
+               const int32_t* leaf_code, const double* root_freq, double* node_vec,
+               double* logl, int32_t* rescales, void* stream);
+
+/* ---- (4) ancestral states: replaces ancestral_state_reconstruction, AR:298-320.
+ * probs may be NULL. */
+int cevb_argmax_states(const double* node_vec, int B, int n_nodes, int n, int32_t* ml_count,
+                       double* ml_prob, double* probs, void* stream);
+
+/* ---- (5) forward stochastic mapping: replaces StochasticMapper.perform_stochastic_mapping,
+ * AR:523-576, with a counter-based Philox4x32-10 generator keyed by (seed, replicate, branch)
+ * so any sharding of replicates gives the same histograms.
+ *   q [n][ldq] one rate matrix; root_probs [n]; parent [n_nodes] (-1 for root);
+ *   preorder [n_nodes] node ids in pre-order (root first); branch_len [n_nodes];
+ *   hist [n_nodes][8][n_bins] uint32 += number of replicates with that many events (bin 0 is
+ *   NOT written: it is n_reps minus the rest); sums [n_nodes][8][2] uint64 += (sum, sum sq).
+ *   state_scratch: n_nodes * rep_chunk uint16.  base_number: 0 = None. */
+int cevb_stoch_map(const double* q, int n, const double* root_probs, int n_nodes,
+                   const int32_t* parent, const int32_t* preorder, const double* branch_len,
+                   int base_number, unsigned long long seed, long long rep_begin,
+                   long long rep_end, int n_bins, uint32_t* hist, unsigned long long* sums,
+                   uint16_t* state_scratch, long long rep_chunk, unsigned long long* n_events,
+                   void* stream);
+
+/* One branch, one replicate, with every event recorded: replaces
+ * StochasticMapper.simulate_events_on_branch, AR:467-521.  ev_* hold max_events entries;
+ * out[0] = number of events simulated (may exceed max_events), out[1] = end state. */
+int cevb_stoch_branch_trace(const double* q, int n, int start_state, double t, int base_number,
+                            unsigned long long seed, unsigned long long replicate, int max_events,
+                            double* ev_time, int32_t* ev_from, int32_t* ev_to, int32_t* ev_type,
+                            int32_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHROMEVOL_B200_H */
