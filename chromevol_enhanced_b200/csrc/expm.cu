@@ -168,9 +168,12 @@ __device__ void tile_inverse(const double* D, int ld, double* dinv, int lane) {
 // C(rt, ct) += G(rt) * R(:, ct) for one 8x8 tile of the augmented matrix [Aq | Bp].
 __device__ __forceinline__ void gj_update_tile(double* Aq, double* Bp, const double* rst, int ldw,
                                                int ldr, int n8, int rt, int ct, double a0,
-                                               double a1, int g, int t, int sg, double& gmax) {
+                                               double a1, int g, int t, int sg, bool pivot_rows,
+                                               double& gmax) {
     double* Cp = ((ct < n8) ? (Aq + ct * 8) : (Bp + (ct - n8) * 8)) + (size_t)(rt * 8 + g) * ldw;
-    double c0 = Cp[t], c1 = Cp[t + 4];
+    // pivot rows become Dinv * R outright (G holds Dinv there); forming them as
+    // R + (Dinv - I) R would cancel two O(b0 ~ 6e16) numbers into an O(1) result.
+    double c0 = pivot_rows ? 0.0 : Cp[t], c1 = pivot_rows ? 0.0 : Cp[t + 4];
     const double b0 = rst[t * ldr + ct * 8 + sg];
     const double b1 = rst[(4 + t) * ldr + ct * 8 + sg];
     dmma884(c0, c1, a0, b0);
@@ -429,12 +432,12 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
                 if (warp == 0) tile_inverse(Aq + (size_t)k0 * ldw + k0, ldw, dcur, lane);
                 __syncthreads();
             }
-            // G = -(column panel) * Dinv, with (Dinv - I) in the pivot rows; R = pivot rows
+            // G = -(column panel) * Dinv, with Dinv itself in the pivot rows; R = pivot rows
             for (int i2 = tid; i2 < npad * 8; i2 += NT) {
                 const int i = i2 >> 3, c = i2 & 7;
                 double gv;
                 if (i >= k0 && i < k0 + 8) {
-                    gv = dcur[(i - k0) * 8 + c] - ((i - k0) == c ? 1.0 : 0.0);
+                    gv = dcur[(i - k0) * 8 + c];
                 } else {
                     const double* ar = Aq + (size_t)i * ldw + k0;
                     double acc = 0.0;
@@ -460,7 +463,7 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
             if (warp == 0 && lookahead) {
                 const int rt = kt + 1;
                 const double a0 = gst[(rt * 8 + g) * GLD + t4], a1 = gst[(rt * 8 + g) * GLD + 4 + t4];
-                gj_update_tile(Aq, Bp, rst, ldw, ldr, n8, rt, kt + 1, a0, a1, g, t4, sg, gmax);
+                gj_update_tile(Aq, Bp, rst, ldw, ldr, n8, rt, kt + 1, a0, a1, g, t4, sg, false, gmax);
                 __syncwarp();
                 tile_inverse(Aq + (size_t)(k0 + 8) * ldw + k0 + 8, ldw, dinv + ((kt + 1) & 1) * 64, lane);
             }
@@ -478,7 +481,8 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
                         for (int q = 0; q < 4; ++q) {
                             const int ct = ct_lo + ch * 4 + q;
                             if (ct < 2 * n8 && !(lookahead && rt == kt + 1 && ct == kt + 1))
-                                gj_update_tile(Aq, Bp, rst, ldw, ldr, n8, rt, ct, a0, a1, g, t4, sg, gmax);
+                                gj_update_tile(Aq, Bp, rst, ldw, ldr, n8, rt, ct, a0, a1, g, t4, sg,
+                                               rt == kt, gmax);
                         }
                     }
                 }

@@ -85,7 +85,8 @@ def test_p_non_generator_and_corners():
     from chromevol_enhanced_b200 import synthetic
     from chromevol_enhanced_b200.engine import transition_matrices
     rows = synthetic.random_param_rows(16, seed=9, linear='mixed', corners=6)
-    times = np.array([0.003, 0.05, 0.3])
+    rows[-1, :8] = [10, 10, 10, 10, 10, 10, 10, -1.0]      # overflows to NaN at t = 0.758
+    times = np.array([0.003, 0.05, 0.758])
     P, m, s, flags = transition_matrices(rows, times, 101, return_info=True)
     n_identity = 0
     for b in range(rows.shape[0]):

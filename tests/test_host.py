@@ -1,0 +1,126 @@
+"""CPU: host-side logic -- Newick reader, tree flattening, parameter marshalling, histogram
+statistics, and that the C-ABI library loads and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, make_tree
+
+
+def test_newick_format1_semantics(shipped):
+    newick, counts = shipped
+    tree = make_tree(newick)
+    nodes = list(tree.traverse())
+    assert len(nodes) == 74 and len(tree) == 38
+    assert tree.name == "Deuterostomia" and [c.name for c in tree.children] == \
+        ["Pecten_maximus", "Ambulacraria", "Branchiostoma_floridae"]
+    assert tree.children[0].dist == pytest.approx(0.562046)
+    # level-order is the default traversal and the reference CSV's row order
+    assert [nd.name for nd in nodes][:4] == ["Deuterostomia", "Pecten_maximus", "Ambulacraria",
+                                             "Branchiostoma_floridae"]
+    t = make_tree("((A,B:0.5)X,(C:1e-3,'D d':2)[&&NHX:x=1]:0.25,E)R:7;")
+    by = {nd.name: nd for nd in t.traverse()}
+    assert by["A"].dist == 1.0 and by["B"].dist == 0.5 and by["X"].dist == 1.0
+    assert by["D d"].dist == 2.0 and by["R"].dist == 7.0 and by["R"].is_root()
+    assert [nd.name for nd in t.traverse("preorder")] == ["R", "X", "A", "B", "", "C", "D d", "E"]
+    assert [nd.name for nd in t.traverse("postorder")] == ["A", "B", "X", "C", "D d", "", "E", "R"]
+    assert [leaf.name for leaf in t] == ["A", "B", "C", "D d", "E"]
+    again = make_tree(t.write())
+    assert [nd.name for nd in again.traverse()] == [nd.name for nd in t.traverse()]
+    with pytest.raises(ValueError):
+        make_tree("((A,B);")
+
+
+def test_flatten_levels_and_codes():
+    from chromevol_enhanced_b200.flatten import FlatTree
+    t = make_tree("((A:0.1,B:0.1):0.05,(C:0.1,D:0.1,E:0.3)X:0.05,F:0,G:-2,H);")
+    f = FlatTree(t, {"A": 22, "B": 24, "C": 20, "D": 99, "F": 3.0, "G": float("nan"), "H": -1}, 34)
+    assert f.n_nodes == 11 and f.root == 0 and f.parent[0] == -1
+    names = [nd.name for nd in f.nodes]
+    code = dict(zip(names, f.leaf_code.tolist()))
+    assert code["A"] == 22 and code["D"] == 34 and code["E"] == -1 and code["F"] == 3
+    assert code["G"] == 34 and code["H"] == 34 and code["X"] == -2       # AR:204-211
+    # children precede parents level by level; file order kept in the CSR lists
+    seen = set(np.flatnonzero(f.leaf_code != -2).tolist())
+    for lv in range(f.n_levels):
+        for node in f.level_nodes[f.level_off[lv]:f.level_off[lv + 1]]:
+            kids = f.child_idx[f.child_off[node]:f.child_off[node + 1]]
+            assert set(kids.tolist()) <= seen
+        seen |= set(f.level_nodes[f.level_off[lv]:f.level_off[lv + 1]].tolist())
+    assert f.level_nodes[-1] == 0
+    # G has a negative length -> 1e-6 for the likelihood (AR:224-227); H's missing length is 1.0
+    g, h = names.index("G"), names.index("H")
+    assert f.t_unique[f.branch_of[g]] == 1e-6 and f.t_unique[f.branch_of[h]] == 1.0
+    assert f.dist_raw[g] == -2.0
+    assert f.preorder[0] == 0 and sorted(f.preorder.tolist()) == list(range(11))
+    assert f.n_t == len(set(f.dist_eff[1:].tolist()))
+
+
+def test_params_to_row_layout():
+    from chromevol_enhanced_b200.engine import params_to_row, PARAM_ORDER
+    from chromevol_enhanced_b200 import MODEL_PARAMETER_NAMES
+    assert PARAM_ORDER[:8] == MODEL_PARAMETER_NAMES
+    row = params_to_row({'gain': 1, 'loss': 2, 'dupl': 3, 'demidupl_gain': 4, 'demidupl_loss': 5,
+                         'base_number': None, 'base_number_gain': 6, 'base_number_loss': 7,
+                         'linear_rate': -0.5})
+    assert row.tolist() == [1, 2, 3, 4, 5, 6, 7, -0.5, 0]
+    assert params_to_row({'base_number': 7})[8] == 7.0
+
+
+def test_percentiles_from_histogram_match_numpy():
+    from chromevol_enhanced_b200.mapper import _percentile_from_hist
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        x = rng.poisson(rng.uniform(0.01, 3), size=rng.integers(1, 400))
+        h = np.bincount(x, minlength=32)
+        for q in (2.5, 50, 97.5):
+            assert _percentile_from_hist(h, len(x), q) == np.percentile(x, q)
+
+
+def test_abi_library_loads_and_exports_header_symbols():
+    from chromevol_enhanced_b200 import _build, _lib
+    _build.build()
+    lib = ctypes.CDLL(_build.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "chromevol_b200.h")).read()
+    declared = set(re.findall(r"\b(cevb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.HEADER_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    typed = _lib.load()
+    assert typed.cevb_abi_version() == 1
+    assert typed.cevb_ldq(101) == 102 and typed.cevb_ldp(36) == 36
+
+
+def test_product_path_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import chromevol_enhanced_b200 as cev
+    from chromevol_enhanced_b200._lib import CevbError
+    with pytest.raises(CevbError):
+        cev.ChromEvolutionModel(10).build_transition_rate_matrix()
+    t = make_tree("(A:1,B:1);")
+    calc = cev.ChromEvolLikelihoodCalculator(t, {"A": 3, "B": 4}, cev.ChromEvolutionModel(10))
+    with pytest.raises(CevbError):
+        calc.calculate_total_log_likelihood()
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "chromevol_enhanced_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+\.*oracle", src, flags=re.M), fn
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_synthetic_generators_are_seeded():
+    from chromevol_enhanced_b200 import synthetic
+    a, b = synthetic.random_tree(50, seed=3), synthetic.random_tree(50, seed=3)
+    assert a.write() == b.write() and len(a) == 50
+    assert len({nd.dist for nd in a.traverse()}) == 99
+    r1, r2 = synthetic.random_param_rows(8, 4, corners=2), synthetic.random_param_rows(8, 4, corners=2)
+    assert np.array_equal(r1, r2) and abs(r1[-1, 7]) == 1.0
