@@ -44,7 +44,7 @@ def test_tree_likelihood_live(AR):
         ll_ref = calc.calculate_total_log_likelihood()
         calc.ancestral_state_reconstruction()
         t_or = Tree(nw, format=1)
-        ll, vectors, _ = O.log_likelihood(t_or, counts, 30, O.default_params(**kw))
+        ll, vectors, _ = O.log_likelihood(t_or, counts, 30, O.default_params(**kw), np.ones(31) / 31)
         assert ll == ll_ref
         for a, b in zip(t_ref.traverse(), t_or.traverse()):
             assert np.array_equal(calc.likelihoods[id(a)], vectors[id(b)])
