@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Benchmark of the chromosome-number likelihood hot path (BASELINE.json metric:
+tree logL evals/sec, 1k taxa, N=100; expm FP64 TFLOP/s).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm
+
+A "step" is one pass of the hot path (rate matrices -> P(t) for every branch -> pruning ->
+logL) over one batch of synthetic parameter vectors on the 1,000-taxon / N=100 tree.  The
+workload at N=1 is the per-GPU share of BASELINE configs[2] (4,096 vectors over 8 GPUs = 512
+per GPU per step, weak scaling); the single-vector case (configs[1]) is reported beside it.
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TAXA = 1000
+MAX_CHR = 100
+TREE_SEED, COUNT_SEED, PARAM_SEED = 1, 2, 4
+METRIC = "tree_logL_evals_per_sec_1k_taxa_N100"
+UNIT = "evals/s"
+
+
+def build_workload(per_gpu_batch, rank):
+    from chromevol_enhanced_b200 import synthetic
+    tree = synthetic.random_tree(N_TAXA, seed=TREE_SEED)
+    counts = synthetic.simulate_tip_counts(tree, MAX_CHR, seed=COUNT_SEED)
+    rows = synthetic.random_param_rows(per_gpu_batch, seed=PARAM_SEED + 1000 * rank, linear='positive')
+    return tree, counts, rows
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "power_w_max": float(max(power)) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One host process: faithful oracle evaluations (Q rebuilt per branch like AR:141)."""
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["OMP_NUM_THREADS"] = "1"
+    newick, counts, rows = args
+    from oracle import chromevol_oracle as O
+    from chromevol_enhanced_b200 import synthetic
+    from chromevol_enhanced_b200.newick import Tree
+    tree = Tree(newick, format=1)
+    t0 = time.perf_counter()
+    out = []
+    for row in rows:
+        ll, _, _ = O.log_likelihood(tree, counts, MAX_CHR, synthetic.row_to_dict(row), faithful_q=True)
+        out.append(ll)
+    return time.perf_counter() - t0, out
+
+
+def cpu_reference_throughput(tree, counts, rows, evals_per_core=1, cores=None):
+    """The reference's numpy/scipy algorithm (oracle port) on the host cores: one process per
+    core, each evaluating a disjoint slice of the batch.  Returns (evals/s, cores, n_evals, logLs)."""
+    import multiprocessing as mp
+    cores = cores or max(1, min(os.cpu_count() or 1, 32))
+    n_eval = cores * evals_per_core
+    take = np.resize(np.arange(rows.shape[0]), n_eval)
+    chunks = [rows[take[c * evals_per_core:(c + 1) * evals_per_core]] for c in range(cores)]
+    newick = tree.write(dist_formatter="%.17g")
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(newick, counts, ch) for ch in chunks])
+    wall = time.perf_counter() - t0
+    busy = max(r[0] for r in res)
+    lls = [x for r in res for x in r[1]]
+    return n_eval / busy, cores, n_eval, lls, wall
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    tree, counts, rows = build_workload(max(64, args.batch), 0)
+    per_step = []
+    cores = None
+    for step in range(args.warmup + args.steps):
+        eps, cores, n_eval, _, wall = cpu_reference_throughput(
+            tree, counts, rows[step % 8::8] if rows.shape[0] >= 64 else rows, evals_per_core=1)
+        if step >= args.warmup:
+            per_step.append((eps, n_eval, wall))
+    value = float(np.mean([p[0] for p in per_step]))
+    ms = float(np.mean([p[1] / p[0] for p in per_step]) * 1e3)
+    sample = (f"{per_step[0][1]} evaluations per step (1 per host process, {cores} processes), "
+              f"faithful per-branch Q rebuild + scipy.linalg.expm + numpy pruning")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, world):
+    return {"workload": f"BASELINE configs[2] per-GPU share: synthetic {N_TAXA}-taxon tree, max count "
+                        f"N={MAX_CHR} (n={MAX_CHR + 1} states, 1998 branches), {args.batch} parameter "
+                        f"vectors per GPU per step (rates LogUniform(1e-3,10), linear_rate U(0,0.1))",
+            "per_gpu_batch": args.batch, "global_batch": args.batch * world,
+            "tree_seed": TREE_SEED, "param_seed": PARAM_SEED, "parallelism": f"dp{world} (vectors sharded)",
+            "l2": "per-step working set (P: 163 MB per vector) far exceeds the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from chromevol_enhanced_b200 import distributed as D
+    from chromevol_enhanced_b200.engine import LikelihoodEngine
+    from chromevol_enhanced_b200.flatten import FlatTree
+
+    rank, world, local = D.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    tree, counts, rows = build_workload(args.batch, rank)
+    flat = FlatTree(tree, counts, MAX_CHR)
+    eng = LikelihoodEngine(flat, device=dev, max_workspace_bytes=args.workspace_gb << 30)
+    B = rows.shape[0]
+    d_rows = torch.as_tensor(rows, device=dev)
+    h_rows = torch.as_tensor(rows).pin_memory()
+    h_out = torch.empty(B, dtype=torch.float64).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        ll = eng.log_likelihood(d_rows)
+        if world > 1:
+            ll = D.all_gather_ragged(ll, B * world, world)
+        return ll
+
+    def step_e2e():
+        d = h_rows.to(dev, non_blocking=True)
+        ll = eng.log_likelihood(d)
+        if world > 1:
+            full = D.all_gather_ragged(ll, B * world, world)
+            h_out.copy_(full[rank * B:(rank + 1) * B], non_blocking=False)
+        else:
+            h_out.copy_(ll, non_blocking=False)
+        return h_out
+
+    # ---- device-resident timing ("value")
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        ll = step_resident()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_res = D.max_across_ranks(ev0.elapsed_time(ev1) * 1e-3, dev)
+    n_chunks = eng.n_chunks
+    # Pade orders / squaring counts the device chose, from one extra untimed step (deterministic)
+    eng.keep_info, eng.info_log = True, []
+    step_resident()
+    barrier()
+    eng.keep_info = False
+    info_log = eng.info_log
+
+    # ---- per-stage timing with CUDA events on the launching stream (roofline numerators)
+    eng.stage_events = []
+    barrier()
+    for _ in range(args.steps):
+        step_resident()
+    barrier()
+    stage_ms = {}
+    for name, a, b in eng.stage_events:
+        stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b)
+    eng.stage_events = None
+
+    # ---- end-to-end through the public call with host buffers ("e2e")
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    ev1.record()
+    barrier()
+    t_e2e = D.max_across_ranks(max(ev0.elapsed_time(ev1) * 1e-3, 0.0), dev)
+    del t0
+
+    # ---- single-vector latency, BASELINE configs[1] (logL + ancestral states)
+    one = d_rows[:1].clone()
+    from chromevol_enhanced_b200 import synthetic
+    one.copy_(torch.as_tensor(synthetic.default_param_row()[None], device=dev))
+    for _ in range(3):
+        eng.log_likelihood(one)
+        eng.ancestral_states(0, want_probs=False)
+    barrier()
+    ev0.record()
+    reps1 = 10
+    for _ in range(reps1):
+        eng.log_likelihood(one)
+        eng.ancestral_states(0, want_probs=False)
+    ev1.record()
+    barrier()
+    t_single = ev0.elapsed_time(ev1) * 1e-3 / reps1
+
+    if rank != 0:
+        return 0
+
+    # ---- algorithmic work of the timed region
+    n = MAX_CHR + 1
+    infos = np.concatenate([x.reshape(-1) for x in info_log]) if info_log else np.zeros(0, dtype=np.int32)
+    m_arr, s_arr, fl_arr = infos & 0xff, (infos >> 8) & 0xff, infos >> 16
+    live = (fl_arr & 1) == 0
+    flops_per_step = float(np.sum((2.0 * (6 + s_arr[live]) + 8.0 / 3.0) * n ** 3))
+    expm_s = stage_ms.get("expm", 0.0) * 1e-3 / max(args.steps, 1)
+    prune_s = stage_ms.get("prune", 0.0) * 1e-3 / max(args.steps, 1)
+    prep_s = stage_ms.get("prepare", 0.0) * 1e-3 / max(args.steps, 1)
+    launches_expm = max(n_chunks, 1)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # FP64 tensor peak: MEASURED_PEAKS.json has no FP64 figure; measure cuBLAS DGEMM here
+    a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    torch.matmul(a, a)
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, a)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e-3)
+    fp64_peak = 2 * 8192 ** 3 / best / 1e12
+    del a
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
+    achieved = flops_per_step / expm_s / 1e12 if expm_s > 0 else None
+    prune_bytes = flat.algorithmic_prune_bytes() * B
+    prune_gbs = prune_bytes / prune_s / 1e9 if prune_s > 0 else None
+    s_hist = {int(k): int(v) for k, v in zip(*np.unique(s_arr[live], return_counts=True))}
+    m_hist = {int(k): int(v) for k, v in zip(*np.unique(m_arr[live], return_counts=True))}
+
+    # ---- CPU baseline (oracle port) on the host cores: bounded sample
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        eps, cores, n_eval, cpu_ll, wall = cpu_reference_throughput(tree, counts, rows, evals_per_core=1)
+        gpu_ll = ll.cpu().numpy()
+        take = np.resize(np.arange(rows.shape[0]), n_eval)
+        rel = float(np.max(np.abs(gpu_ll[take] - np.array(cpu_ll)) / np.abs(np.array(cpu_ll))))
+        cpu = {"value": eps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_eval} of the step's {B} vectors, one per host process "
+                         f"(faithful per-branch Q rebuild + scipy expm + numpy pruning), {wall:.1f} s wall",
+               "max_rel_logL_diff_vs_gpu": rel}
+
+    total = B * world * args.steps
+    line = {
+        "metric": METRIC, "value": total / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "e2e": {"value": total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 9 * 8),
+                "d2h_bytes_per_step": int(B * 8), "ms_per_step": t_e2e / args.steps * 1e3},
+        "gpu_launches": int(args.steps * n_chunks * eng.launches_per_chunk()),
+        "roofline": {"kernel": "expm_branch_kernel", "bound": "tensor", "achieved": achieved,
+                     "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": (achieved / fp64_peak) if achieved else None,
+                     "traffic": (traffic or {}).get("expm_branch_kernel"),
+                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                     "algorithmic_flops_per_launch": flops_per_step / launches_expm,
+                     "launch_ms": expm_s / launches_expm * 1e3,
+                     "pade_order_hist": m_hist, "squarings_hist": s_hist},
+        "roofline_prune": {"kernel": "prune_level_kernel", "bound": "hbm", "achieved": prune_gbs,
+                           "peak": hbm_peak, "unit": "GB/s", "frac": (prune_gbs / hbm_peak) if prune_gbs else None,
+                           "traffic": (traffic or {}).get("prune_level_kernel"), "peak_source": hbm_src,
+                           "algorithmic_bytes_per_step": prune_bytes, "ms_per_step": prune_s * 1e3},
+        "stage_ms_per_step": {"prepare": prep_s * 1e3, "expm": expm_s * 1e3, "prune": prune_s * 1e3},
+        "single_vector": {"workload": "BASELINE configs[1]: one vector logL + argmax states",
+                          "ms": t_single * 1e3, "evals_per_s": 1.0 / t_single},
+        "repivot_events": eng.repivot_events,
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="parameter vectors per GPU per step")
+    ap.add_argument("--workspace-gb", type=int, default=48)
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -98,6 +98,9 @@ class LikelihoodEngine:
         self._cap = 0
         self.last_info = None
         self.repivot_events = 0
+        self.stage_events = None     # set to a list to record (stage, start, end) CUDA events
+        self.keep_info = False       # accumulate (m, s, flags) of every chunk on the host
+        self.info_log = []
 
     # ------------------------------------------------------------------ buffers
     def _ensure(self, cap):
@@ -119,39 +122,58 @@ class LikelihoodEngine:
                                device=self.device)
 
     # ------------------------------------------------------------------ stages (async)
+    def _mark(self, stage, start=None):
+        """Record a CUDA event on the launching stream when stage timing is on."""
+        if self.stage_events is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        if start is not None:
+            self.stage_events.append((stage, start, ev))
+        return ev
+
     def _transition_matrices(self, ws, nb, full_pivot=0):
         lib, st = self.lib, _stream_ptr()
+        e0 = self._mark("prepare")
         _lib.check(lib.cevb_build_q(_lib.ptr(ws.params), nb, self.n, _lib.ptr(ws.pw), st),
                    "cevb_build_q")
         _lib.check(lib.cevb_expm_prepare(_lib.ptr(ws.pw), nb, self.n, _lib.ptr(ws.norms),
                                          _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt), st),
                    "cevb_expm_prepare")
+        e1 = self._mark("prepare", e0)
         _lib.check(lib.cevb_expm_branches(_lib.ptr(ws.pw), _lib.ptr(ws.norms), _lib.ptr(ws.csc),
                                           _lib.ptr(ws.csc_cnt), _lib.ptr(self.d_t), nb,
                                           self.flat.n_t, self.n, _lib.ptr(ws.P), _lib.ptr(ws.info),
                                           _lib.ptr(ws.scratch), _lib.ptr(ws.counter), full_pivot,
                                           st), "cevb_expm_branches")
+        self._mark("expm", e1)
 
     def _prune(self, ws, nb, d_root_freq):
         f = self.flat
+        e0 = self._mark("prune")
         _lib.check(self.lib.cevb_prune(
             _lib.ptr(ws.P), nb, f.n_t, self.n, f.n_nodes, f.root, _lib.ptr(self.d_level_nodes),
             self.h_level_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), f.n_levels,
             _lib.ptr(self.d_child_off), _lib.ptr(self.d_child_idx), _lib.ptr(self.d_branch_of),
             _lib.ptr(self.d_leaf_code), _lib.ptr(d_root_freq), _lib.ptr(self._node_vec),
             _lib.ptr(self._logl), _lib.ptr(self._rescales), _stream_ptr()), "cevb_prune")
+        self._mark("prune", e0)
 
-    def _run_chunk(self, d_params_chunk, d_root_freq, check_growth=True):
+    def _run_chunk(self, d_params_chunk, d_root_freq, full_pivot=0):
         nb = d_params_chunk.shape[0]
         ws = self._ws
         ws.params[:nb].copy_(d_params_chunk)
-        self._transition_matrices(ws, nb, 0)
-        if check_growth:
-            flagged = bool(((ws.info[:nb] >> 16) & INFO_GROWTH).any().item())
-            if flagged:  # rare: redo the chunk with full partial pivoting
-                self.repivot_events += 1
-                self._transition_matrices(ws, nb, 1)
+        self._transition_matrices(ws, nb, full_pivot)
+        # element-growth monitor of the tile-pivoted solve: OR into a device flag, no host sync
+        self._growth_flag |= ((ws.info[:nb] >> 16) & INFO_GROWTH).any()
+        if self.keep_info:
+            self.info_log.append(ws.info[:nb].cpu().numpy().copy())
         self._prune(ws, nb, d_root_freq)
+
+    def launches_per_chunk(self):
+        """Kernel launches of ours per chunk: build_q, 4 power GEMMs, norms, expm, leaf init and
+        one pruning kernel per non-empty level."""
+        return 8 + int(np.count_nonzero(np.diff(self.flat.level_off)))
 
     # ------------------------------------------------------------------ public
     def log_likelihood(self, params, root_freq=None, check_growth=True):
@@ -168,11 +190,19 @@ class LikelihoodEngine:
         out = torch.empty(B, dtype=torch.float64, device=self.device)
         self.rescale_counts = torch.zeros(B, dtype=torch.int32, device=self.device)
         self._ensure(min(self.chunk, B))
-        for lo in range(0, B, self._cap):
-            hi = min(B, lo + self._cap)
-            self._run_chunk(d_params[lo:hi], d_root, check_growth)
-            out[lo:hi].copy_(self._logl[:hi - lo])
-            self.rescale_counts[lo:hi].copy_(self._rescales[:hi - lo])
+        self._growth_flag = torch.zeros((), dtype=torch.bool, device=self.device)
+        for full_pivot in (0, 1):
+            for lo in range(0, B, self._cap):
+                hi = min(B, lo + self._cap)
+                self._run_chunk(d_params[lo:hi], d_root, full_pivot)
+                out[lo:hi].copy_(self._logl[:hi - lo])
+                self.rescale_counts[lo:hi].copy_(self._rescales[:hi - lo])
+            # one host read at the end; a tripped monitor (not seen in practice) redoes the batch
+            # with full partial pivoting in every panel
+            if full_pivot or not check_growth or not bool(self._growth_flag.item()):
+                break
+            self.repivot_events += 1
+        self.n_chunks = (B + self._cap - 1) // self._cap
         self.last_batch = B
         return out
 

@@ -1,0 +1,153 @@
+"""GPU: the Philox stochastic-mapping simulator -- statistical parity with the reference's
+replicate statistics (golden) and with the oracle simulator, shard invariance, classification."""
+import numpy as np
+import pytest
+
+from conftest import make_tree
+from oracle import chromevol_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+OPT_FULL = dict(gain=2.1342596548720283, loss=0.2677580853199203, dupl=2.016554428743558,
+                demidupl_gain=0.38097654656835955, demidupl_loss=1.1888333123910255,
+                base_number_gain=0.01, base_number_loss=0.01, linear_rate=-0.03935220722444711)
+
+
+def _run(tree, params, N, root_probs, reps, seed, **kw):
+    from chromevol_enhanced_b200.engine import params_to_row
+    from chromevol_enhanced_b200.flatten import FlatTree
+    from chromevol_enhanced_b200 import mapper
+    flat = FlatTree(tree, {}, N)
+    bn = params.get('base_number') or 0
+    return flat, mapper.simulate(flat, params_to_row(params), N + 1, root_probs, reps, seed,
+                                 base_number=bn, **kw)
+
+
+def test_mean_counts_match_reference_replicates(golden, shipped):
+    """z-test of per-(branch, type) mean event counts: 200k device replicates against the 4,000
+    reference replicates stored in the golden file (alpha ~ 1e-3 overall)."""
+    arrays, meta = golden
+    newick, _ = shipped
+    tree = make_tree(newick)
+    R = 200_000
+    flat, res = _run(tree, O.default_params(**OPT_FULL), 35, arrays["map_root_probs"], R, seed=11)
+    assert not res.overflowed()
+    mean = res.sums[:, :, 0] / R
+    Rref = meta["mapping"]["replicates"]
+    var_ref = arrays["map_std"] ** 2
+    se = np.sqrt(var_ref / Rref + var_ref / R)
+    active = arrays["map_total"] + res.sums[:, :, 0] > 0
+    z = np.abs(mean - arrays["map_mean"])[active] / np.maximum(se[active], 2e-3)
+    assert z.max() < 5.0, z.max()
+    # population std (np.std, ddof=0) agrees too
+    std = np.sqrt(np.maximum(res.sums[:, :, 1] / R - mean ** 2, 0))
+    big = arrays["map_mean"] > 0.2
+    assert np.allclose(std[big], arrays["map_std"][big], rtol=0.08)
+    # event types that cannot occur without a base number stay empty
+    assert res.sums[:, 3:5, 0].sum() == 0
+    assert res.n_events == int(res.sums[:, :, 0].sum())
+
+
+def test_count_distribution_against_oracle_simulator():
+    """Chi-square of the per-branch count histograms against the CPU oracle simulator."""
+    from chromevol_enhanced_b200 import synthetic
+    tree = synthetic.random_tree(12, seed=3, mean_len=0.3)
+    params = O.default_params(gain=1.2, loss=0.7, dupl=0.4, demidupl_gain=0.3, demidupl_loss=0.2,
+                              base_number=3, base_number_gain=0.5, base_number_loss=0.4)
+    N = 20
+    root_probs = np.zeros(N + 1)
+    root_probs[[6, 7, 9]] = [0.5, 0.3, 0.2]
+    R = 400_000
+    flat, res = _run(tree, params, N, root_probs, R, seed=5)
+    rng = np.random.default_rng(1)
+    Rc = 3000
+    order, out = O.stochastic_mapping_counts(tree, O.build_q(params, N), root_probs, Rc, rng, base_number=3)
+    idx = {id(nd): k for k, nd in enumerate(flat.nodes)}
+    worst = 0.0
+    n_tests = 0
+    for b, nd in enumerate(order):
+        k = idx[id(nd)]
+        for e in range(8):
+            h_gpu = res.hist[k, e, :12].astype(float)
+            h_cpu = np.bincount(np.minimum(out[:, b, e], 11), minlength=12).astype(float)
+            p = h_gpu / R
+            keep = p * Rc >= 5
+            if keep.sum() < 2:
+                continue
+            # lump the rest
+            exp = np.append(p[keep], 1 - p[keep].sum()) * Rc
+            obs = np.append(h_cpu[keep], Rc - h_cpu[keep].sum())
+            good = exp > 1e-9
+            chi2 = float(np.sum((obs[good] - exp[good]) ** 2 / exp[good]))
+            dof = int(good.sum()) - 1
+            worst = max(worst, (chi2 - dof) / np.sqrt(2 * max(dof, 1)))
+            n_tests += 1
+    assert n_tests > 20
+    assert worst < 6.0, worst
+    # all eight event types are exercised with a base number set
+    assert (res.sums[:, :, 0].sum(axis=0) > 0).all()
+
+
+def test_sharding_invariance_and_seed_dependence(shipped, golden):
+    arrays, _ = golden
+    newick, _ = shipped
+    tree = make_tree(newick)
+    p = O.default_params(**OPT_FULL)
+    R = 20_000
+    flat, full = _run(tree, p, 35, arrays["map_root_probs"], R, seed=99)
+    _, a = _run(tree, p, 35, arrays["map_root_probs"], R, seed=99, rep_begin=0, rep_end=7_777, rep_chunk=1024)
+    _, b = _run(tree, p, 35, arrays["map_root_probs"], R, seed=99, rep_begin=7_777, rep_end=R)
+    assert np.array_equal(a.sums + b.sums, full.sums)
+    assert np.array_equal(a.hist[:, :, 1:] + b.hist[:, :, 1:], full.hist[:, :, 1:])
+    _, other = _run(tree, p, 35, arrays["map_root_probs"], R, seed=100)
+    assert not np.array_equal(other.sums, full.sums)
+
+
+def test_zero_and_missing_branch_lengths_record_no_events():
+    tree = make_tree("((A:0.5,B:0)X:-1,(C,D:0.2)Y:0.3)R;")
+    for nd in tree.traverse():
+        if nd.name == "C":
+            nd.dist = None
+    root_probs = np.zeros(11)
+    root_probs[5] = 1.0
+    flat, res = _run(tree, O.default_params(gain=3.0, loss=3.0), 10, root_probs, 4096, seed=1)
+    names = [nd.name for nd in flat.nodes]
+    for nm in ("B", "X", "C"):                      # AR:562-566
+        assert res.sums[names.index(nm)].sum() == 0
+    for nm in ("A", "D", "Y"):
+        assert res.sums[names.index(nm), :, 0].sum() > 0
+
+
+def test_dropin_mapper_summary_and_single_branch(shipped, golden):
+    import chromevol_enhanced_b200 as cev
+    arrays, _ = golden
+    newick, counts = shipped
+    tree = make_tree(newick)
+    model = cev.ChromEvolutionModel(35, custom_params=OPT_FULL)
+    calc = cev.ChromEvolLikelihoodCalculator(tree, counts, model)
+    calc.set_root_frequencies(np.ones(36) / 36)
+    calc.ancestral_state_reconstruction()
+    mapper = cev.StochasticMapper(tree, model, num_mappings=100, seed=4)
+    summary = mapper.perform_stochastic_mapping()
+    assert set(summary) == {id(nd) for nd in tree.traverse() if not nd.is_root()}
+    one = next(iter(summary.values()))
+    assert list(one) == cev.EVENT_TYPES
+    assert set(one['gain']) == {'mean', 'std', 'ci_lower', 'ci_upper', 'total_occurrences'}
+    for nd in tree.traverse():
+        if not nd.is_root():
+            assert nd.expected_gain == summary[id(nd)]['gain']['mean']
+    # percentiles / means are consistent with the raw histogram
+    res = mapper.last_result
+    k = 1
+    counts_k = np.repeat(np.arange(res.n_bins), res.hist[k, 0])
+    s = summary[id(res.flat.nodes[k])]['gain']
+    assert s['mean'] == pytest.approx(counts_k.mean()) and s['std'] == pytest.approx(counts_k.std())
+    assert s['ci_upper'] == np.percentile(counts_k, 97.5) and s['total_occurrences'] == counts_k.sum()
+    events, end = mapper.simulate_events_on_branch(10, 2.0, model.params)
+    assert len(events) > 0 and events[-1]['to_state'] == end
+    t_prev, s_prev = 0.0, 10
+    for ev in events:
+        assert ev['time_on_branch'] > t_prev and ev['from_state'] == s_prev
+        assert ev['type'] == O.classify_event(ev['from_state'], ev['to_state'], None)
+        t_prev, s_prev = ev['time_on_branch'], ev['to_state']
+    assert mapper.simulate_events_on_branch(10, 0.0, model.params) == ([], 10)
