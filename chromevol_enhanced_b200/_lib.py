@@ -45,10 +45,11 @@ _PROTOTYPES = {
                                            _c.c_ulonglong, _c.c_ulonglong, _c.c_int, c_dp, c_dp, c_dp,
                                            c_dp, c_dp, _c.c_void_p]),
     "cevb_diag_fp64_peak": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, c_dp, _c.c_void_p]),
+    "cevb_diag_set_phase_buffer": (_c.c_int, [c_dp]),
 }
 
 # symbols include/chromevol_b200.h declares (the CPU test-suite checks every one is exported)
-HEADER_SYMBOLS = [name for name in _PROTOTYPES if name != "cevb_diag_fp64_peak"]
+HEADER_SYMBOLS = [name for name in _PROTOTYPES if not name.startswith("cevb_diag_")]
 
 
 def library_path():

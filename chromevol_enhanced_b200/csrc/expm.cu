@@ -48,6 +48,7 @@ struct BranchArgs {
     long long M;
     int B, E, n, ldq, ldp, n8, npad, ldw, ldr, use_smem, full_pivot;
     size_t scratch_doubles;  // per CTA
+    unsigned long long* phase_clk;  // optional diagnostics: SM clocks per phase (thread 0 of each CTA)
 };
 
 struct Order {
@@ -194,6 +195,29 @@ __device__ double block_max(double v, double* red) {
     return r;
 }
 
+#define CEVB_PHASE(k)                                                          \
+    do {                                                                       \
+        if (a.phase_clk != nullptr && tid == 0) {                              \
+            const long long _now = clock64();                                  \
+            ph[k] += (unsigned long long)(_now - ph_t);                        \
+            ph_t = _now;                                                       \
+        }                                                                      \
+    } while (0)
+
+// Pade order and squaring count of every (vector, branch) pair, one thread each.
+__global__ void __launch_bounds__(256) order_kernel(const double* __restrict__ norms,
+                                                    const double* __restrict__ t, int E, long long M,
+                                                    int32_t* __restrict__ info) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M) return;
+    const int b = (int)(idx / E), e = (int)(idx - (long long)b * E);
+    const double tb = t[e];
+    Order o = {0, 0, 0};
+    if (tb > 0.0) o = select_order(norms + (size_t)b * CEVB_NNORM, tb);
+    if (o.s > 200) o.fail = 1;
+    info[idx] = o.m | ((o.s & 0xff) << 8) | (o.fail << 16);
+}
+
 __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -222,6 +246,8 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
     uint8_t* tcnt = reinterpret_cast<uint8_t*>(trows + (size_t)CEVB_MAX_SPARSE * n);
 
     const size_t matq = (size_t)n * ldq;
+    unsigned long long ph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long ph_t = clock64();
 
     for (;;) {
         if (tid == 0) {
@@ -237,15 +263,9 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
         const double* pwb = a.pw + (size_t)b * CEVB_NPOW * matq;
         double* Pout = a.P + (size_t)idx * n * a.ldp;
 
-        if (tid == 0) {
-            Order o = {0, 0, 0};
-            if (tb > 0.0) o = select_order(nr, tb);
-            ish[2] = o.m;
-            ish[3] = o.s;
-            ish[4] = o.fail;
-        }
-        __syncthreads();
-        const int m = ish[2], s = ish[3], fail = ish[4];
+        const int code = a.info[idx];   // written by order_kernel: m | s << 8 | fail << 16
+        const int m = code & 0xff, s = (code >> 8) & 0xff, fail = code >> 16;
+        CEVB_PHASE(0);
 
         if (!(tb > 0.0) || fail) {
             // t == 0 -> identity (AR:146-148); selection failure mirrors the reference's
@@ -299,17 +319,18 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
                 bufB[(size_t)i * ldw + j] = v;
             }
         }
+        CEVB_PHASE(1);
         // stage the sparse structure of A = ts * Q (values pre-scaled)
         const bool dense = nr[CEVB_NORM_DENSE] != 0.0;
         if (!dense) {
-            for (int j = tid; j < n; j += NT) tcnt[j] = a.csc_cnt[(size_t)b * n + j];
+            for (int j = tid; j < n; j += NT) tcnt[j] = a.csc_cnt[(size_t)b * 2 * n + j];
             for (int i2 = tid; i2 < CEVB_MAX_SPARSE * n; i2 += NT) {
                 const int c = i2 / n, j = i2 - c * n;
-                const int cnt = a.csc_cnt[(size_t)b * n + j];
+                const int cnt = a.csc_cnt[(size_t)b * 2 * n + j];
                 uint16_t r = 0;
                 double v = 0.0;
                 if (c < cnt) {
-                    r = a.csc[((size_t)b * CEVB_MAX_SPARSE + c) * n + j];
+                    r = a.csc[((size_t)b * 2 * CEVB_MAX_SPARSE + c) * n + j];
                     v = ts * pwb[(size_t)r * ldq + j];
                 }
                 trows[i2] = r;
@@ -317,6 +338,7 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
             }
         }
         __syncthreads();
+        CEVB_PHASE(2);
 
         // ---- 3. U = W * (ts Q), in place in bufA, one warp per row -------------------------
         for (int i = warp; i < npad; i += NW) {
@@ -346,6 +368,7 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
             }
         }
         __syncthreads();
+        CEVB_PHASE(3);
 
         // ---- 4. Aq = V - U (bufA), Bp = V + U (bufB) --------------------------------------
         double* Aq = bufA;
@@ -362,6 +385,7 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
         }
         __syncthreads();
 
+        CEVB_PHASE(4);
         // ---- 5. blocked Gauss-Jordan ------------------------------------------------------
         double gmax = 0.0;
         if (!a.full_pivot) {
@@ -456,6 +480,7 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
                 }
             }
             __syncthreads();
+            CEVB_PHASE(5);
 
             // trailing update: tiles (rt, ct), ct in (kt, 2*n8)
             const int ct_lo = kt + 1;
@@ -488,6 +513,7 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
                 }
             }
             __syncthreads();
+            CEVB_PHASE(6);
         }
 
         // ---- 6. squarings -----------------------------------------------------------------
@@ -525,6 +551,7 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
             dst = tmp;
         }
 
+        CEVB_PHASE(7);
         // ---- 7. floor, renormalise, NaN check, store (AR:153-159) --------------------------
         int nanflag = 0;
         for (int i = warp; i < n; i += NW) {
@@ -571,7 +598,455 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
             a.info[idx] = m | (s << 8) | (flags << 16);
         }
         __syncthreads();
+        CEVB_PHASE(8);
     }
+    if (a.phase_clk != nullptr && tid == 0) {
+        for (int k = 0; k < 10; ++k) atomicAdd(&a.phase_clk[k], ph[k]);
+    }
+}
+
+
+// =========================================================================================
+// Fast path, n <= 104: everything in shared memory, shared-space pointers (LDS/STS), no integer
+// divisions in the loops, 16-byte accesses where rows allow it.
+//   - working matrices have row stride ldw = 8 (mod 16) doubles, so the 16-byte C-fragment
+//     accesses of the Gauss-Jordan update (row g, columns 2t..2t+1) are bank-conflict free;
+//     G (stride 12) and R (stride 4 mod 16) staging tiles serve the A / B fragments.
+//   - U = (ts Q) W is formed row-wise from the compressed rows of Q into REGISTERS (7 rows x 4
+//     column slots per warp), then V -+ U are written straight over W and V.
+//   - the diagonal tile is inverted without a pivot search (one warp, shuffles only); the growth
+//     monitor and a relative pivot-size check guard that choice (full_pivot launches use the
+//     generic kernel above).
+__device__ __forceinline__ int hi_abs(double v) { return __double2hiint(v) & 0x7fffffff; }
+
+// 1/x to full double precision for normal, finite x: hardware seed (about 20 bits) + Newton.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+__device__ int block_max_int(int v, int* red) {
+    v = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = red[0];
+#pragma unroll
+    for (int i = 1; i < NW; ++i) r = max(r, red[i]);
+    __syncthreads();
+    return r;
+}
+
+constexpr int FR = 7;   // rows per warp kept in registers (npad <= 112)
+constexpr int FJ = 4;   // 32-wide column slots per row (npad <= 128)
+
+__device__ __forceinline__ int tile_inverse_fast(const double* D, int ld, double* dinv, int lane) {
+    const int r = lane >> 2, q = lane & 3;
+    double x[4];
+    double dmax = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        x[j] = (q < 2) ? D[r * ld + 4 * q + j] : ((4 * (q - 2) + j) == r ? 1.0 : 0.0);
+        if (q < 2) dmax = fmax(dmax, fabs(x[j]));
+    }
+    dmax = warp_max(dmax);
+    int bad = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double myc = __shfl_sync(0xffffffffu, x[c & 3], (lane & ~3) | (c >> 2));
+        const double pv = __shfl_sync(0xffffffffu, x[c & 3], (c << 2) | (c >> 2));
+        if (!(fabs(pv) >= 1e-6 * dmax)) bad = 1;
+        const double inv = fast_rcp(pv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double pr = __shfl_sync(0xffffffffu, x[j], (c << 2) | q) * inv;
+            x[j] = (r == c) ? pr : fma(-myc, pr, x[j]);
+        }
+    }
+    if (q >= 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dinv[r * 8 + 4 * (q - 2) + j] = x[j];
+    }
+    return bad;
+}
+
+__global__ void __launch_bounds__(NT, 1) expm_branch_fast_kernel(BranchArgs a) {
+    extern __shared__ __align__(16) double smf[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int n = a.n, npad = a.npad, n8 = a.n8, ldw = a.ldw, ldr = a.ldr, ldq = a.ldq, ldp = a.ldp;
+    // augmented matrix [A | B]: npad rows, row stride ldw = 2*npad + 8 (= 8 mod 16 doubles)
+    double* const bufA = smf;
+    double* const bufB = smf + npad;
+    double* const gst = smf + npad * ldw;     // npad x GLD
+    double* const rst = gst + npad * GLD;     // 8 x ldr
+    double* const dinv = rst + 8 * ldr;       // 2 x 64
+    double* const red = dinv + 128;           // 32
+    int* const ish = reinterpret_cast<int*>(red + 32);
+    // compressed-row table of ts*Q, staged in the (not yet used) gst/rst region
+    double* const tval = gst;
+    uint16_t* const tidx = reinterpret_cast<uint16_t*>(tval + CEVB_MAX_SPARSE * n);
+    uint8_t* const tcnt = reinterpret_cast<uint8_t*>(tidx + CEVB_MAX_SPARSE * n);
+
+    const size_t matq = (size_t)n * ldq;
+    __shared__ unsigned long long ph[10];
+    __shared__ long long ph_t;
+    if (tid == 0) {
+        for (int k = 0; k < 10; ++k) ph[k] = 0;
+        ph_t = clock64();
+    }
+
+    for (;;) {
+        if (tid == 0) ish[0] = (int)atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const long long idx = (long long)(unsigned)ish[0];
+        if (idx >= a.M) break;
+        const int b = (int)(idx / a.E), e = (int)(idx - (long long)b * a.E);
+        const double tb = a.t[e];
+        const double* __restrict__ pwb = a.pw + (size_t)b * CEVB_NPOW * matq;
+        double* __restrict__ Pout = a.P + (size_t)idx * n * ldp;
+        const int code = a.info[idx];
+        const int m = code & 0xff, s = (code >> 8) & 0xff, fail = code >> 16;
+        CEVB_PHASE(0);
+
+        if (!(tb > 0.0) || fail) {
+            for (int i = warp; i < n; i += NW)
+                for (int j = lane; j < ldp; j += 32) Pout[(size_t)i * ldp + j] = (i == j) ? 1.0 : 0.0;
+            if (tid == 0)
+                a.info[idx] = fail ? (13 | (CEVB_INFO_NAN_FALLBACK << 16)) : (CEVB_INFO_IDENTITY_T0 << 16);
+            __syncthreads();
+            continue;
+        }
+
+        const double ts = ldexp(tb, -s);
+        const int kmax = (m == 13) ? 6 : (m >> 1);
+        const double* bc = (m == 3) ? c_b3 : (m == 5) ? c_b5 : (m == 7) ? c_b7 : (m == 9) ? c_b9 : c_b13;
+
+        // ---- W -> bufA, V -> bufB: 16-byte loads of the shared powers, all in flight -------
+        {
+            double cw[7], cv[7];
+            double pk = 1.0;
+            const double ts2 = ts * ts;
+#pragma unroll
+            for (int k = 1; k <= 6; ++k) {
+                pk *= ts2;
+                cw[k] = (k <= kmax) ? bc[2 * k + 1] * pk : 0.0;
+                cv[k] = (k <= kmax) ? bc[2 * k] * pk : 0.0;
+            }
+            const double b1 = bc[1], b0 = bc[0];
+            for (int item = warp; item < 2 * npad; item += NW) {
+                const int i = item >> 1, pass = item & 1;
+                const int j = 2 * lane + 64 * pass;
+                if (j >= npad) continue;
+                double2 xx[6];
+                const bool in = (i < n) && (j < ldq);
+                const double2* src = reinterpret_cast<const double2*>(pwb + (size_t)i * ldq + j);
+#pragma unroll
+                for (int k = 1; k <= 6; ++k)
+                    xx[k - 1] = (in && k <= kmax) ? __ldg(src + (size_t)k * (matq >> 1)) : make_double2(0.0, 0.0);
+                double w0 = 0.0, w1 = 0.0, v0 = 0.0, v1 = 0.0;
+#pragma unroll
+                for (int k = 6; k >= 1; --k) {
+                    w0 = fma(cw[k], xx[k - 1].x, w0);
+                    w1 = fma(cw[k], xx[k - 1].y, w1);
+                    v0 = fma(cv[k], xx[k - 1].x, v0);
+                    v1 = fma(cv[k], xx[k - 1].y, v1);
+                }
+                if (i == j) { w0 += b1; v0 += b0; }
+                if (i == j + 1) { w1 += b1; v1 += b0; }
+                *reinterpret_cast<double2*>(bufA + i * ldw + j) = make_double2(w0, w1);
+                *reinterpret_cast<double2*>(bufB + i * ldw + j) = make_double2(v0, v1);
+            }
+        }
+        CEVB_PHASE(1);
+        // ---- stage the compressed rows of ts*Q ------------------------------------------------
+        const bool dense = a.norms[(size_t)b * CEVB_NNORM + CEVB_NORM_DENSE] != 0.0;
+        if (!dense) {
+            const uint16_t* gidx = a.csc + ((size_t)b * 2 + 1) * CEVB_MAX_SPARSE * n;
+            const uint8_t* gcnt = a.csc_cnt + ((size_t)b * 2 + 1) * n;
+            for (int i = tid; i < n; i += NT) tcnt[i] = gcnt[i];
+            for (int c = warp; c < CEVB_MAX_SPARSE; c += NW) {
+                for (int i = lane; i < n; i += 32) {
+                    const int cnt = gcnt[i];
+                    uint16_t k = 0;
+                    double v = 0.0;
+                    if (c < cnt) {
+                        k = gidx[c * n + i];
+                        v = ts * pwb[(size_t)i * ldq + k];
+                    }
+                    tidx[c * n + i] = k;
+                    tval[c * n + i] = v;
+                }
+            }
+        }
+        __syncthreads();
+        CEVB_PHASE(2);
+
+        // ---- U = (ts Q) W, rows held in registers ---------------------------------------------
+        double u[FR][FJ];
+#pragma unroll
+        for (int r = 0; r < FR; ++r) {
+            const int i = warp + NW * r;
+#pragma unroll
+            for (int jj = 0; jj < FJ; ++jj) u[r][jj] = 0.0;
+            if (i < n) {
+                if (!dense) {
+                    const int cnt = tcnt[i];
+                    for (int c = 0; c < cnt; ++c) {
+                        const double av = tval[c * n + i];
+                        const double* wr = bufA + (int)tidx[c * n + i] * ldw + lane;
+#pragma unroll
+                        for (int jj = 0; jj < FJ; ++jj)
+                            if (lane + 32 * jj < npad) u[r][jj] = fma(av, wr[32 * jj], u[r][jj]);
+                    }
+                } else {
+                    for (int k = 0; k < n; ++k) {
+                        const double av = ts * pwb[(size_t)i * ldq + k];
+                        const double* wr = bufA + k * ldw + lane;
+#pragma unroll
+                        for (int jj = 0; jj < FJ; ++jj)
+                            if (lane + 32 * jj < npad) u[r][jj] = fma(av, wr[32 * jj], u[r][jj]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        CEVB_PHASE(3);
+        // ---- Aq = V - U -> bufA, Bp = V + U -> bufB -------------------------------------------
+        double* const Aq = bufA;
+        double* const Bp = bufB;
+        int gmax0 = 0;   // high words of |x|: a monotone integer proxy for magnitude (no FP64 pipe)
+#pragma unroll
+        for (int r = 0; r < FR; ++r) {
+            const int i = warp + NW * r;
+            if (i < npad) {
+#pragma unroll
+                for (int jj = 0; jj < FJ; ++jj) {
+                    const int j = lane + 32 * jj;
+                    if (j < npad) {
+                        const double v = Bp[i * ldw + j];
+                        const double qm = v - u[r][jj], pm = v + u[r][jj];
+                        Aq[i * ldw + j] = qm;
+                        Bp[i * ldw + j] = pm;
+                        gmax0 = max(gmax0, max(hi_abs(qm), hi_abs(pm)));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        CEVB_PHASE(4);
+
+        // ---- blocked Gauss-Jordan -------------------------------------------------------------
+        int gmax = 0;
+        int pivbad = 0;
+        if (warp == 0) pivbad |= tile_inverse_fast(Aq, ldw, dinv, lane);
+        __syncthreads();
+        for (int kt = 0; kt < n8; ++kt) {
+            const int k0 = kt * 8;
+            const double* dcur = dinv + (kt & 1) * 64;
+            // G = -(column panel) * Dinv (Dinv itself in the pivot rows)
+            for (int i2 = tid; i2 < npad * 8; i2 += NT) {
+                const int i = i2 >> 3, c = i2 & 7;
+                double gv;
+                if ((i >> 3) == kt) {
+                    gv = dcur[(i - k0) * 8 + c];
+                } else {
+                    const double2* ar = reinterpret_cast<const double2*>(Aq + i * ldw + k0);
+                    const double2 x0 = ar[0], x1 = ar[1], x2 = ar[2], x3 = ar[3];
+                    double acc = x0.x * dcur[c];
+                    acc = fma(x0.y, dcur[8 + c], acc);
+                    acc = fma(x1.x, dcur[16 + c], acc);
+                    acc = fma(x1.y, dcur[24 + c], acc);
+                    acc = fma(x2.x, dcur[32 + c], acc);
+                    acc = fma(x2.y, dcur[40 + c], acc);
+                    acc = fma(x3.x, dcur[48 + c], acc);
+                    acc = fma(x3.y, dcur[56 + c], acc);
+                    gv = -acc;
+                }
+                gst[i * GLD + c] = gv;
+            }
+            // R = pivot rows, columns (k0 + 8) .. 2 npad of the augmented matrix
+            {
+                const int r = tid >> 6, c0 = tid & 63;
+                const double* ra = Aq + (k0 + r) * ldw;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const int cc = k0 + 8 + c0 + 64 * p;
+                    if (cc < 2 * npad) rst[r * ldr + cc] = ra[cc];
+                }
+            }
+            __syncthreads();
+            CEVB_PHASE(5);
+
+            const int ct_lo = kt + 1;
+            const bool lookahead = (kt + 1 < n8);
+            const double* const gA = gst + g * GLD + t4;        // A fragments: + rt*8*GLD (+4)
+            const double* const rB = rst + t4 * ldr + g;        // B fragments: + ct*8 (+4*ldr)
+            double* const cB = Aq + g * ldw + 2 * t4;           // C fragments: + rt*8*ldw + ct*8
+            if (warp == 0 && lookahead) {
+                const int rt = kt + 1;
+                const double a0 = gA[rt * 8 * GLD], a1 = gA[rt * 8 * GLD + 4];
+                double2* cp = reinterpret_cast<double2*>(cB + rt * 8 * ldw + rt * 8);
+                double2 c = *cp;
+                dmma884(c.x, c.y, a0, rB[rt * 8]);
+                dmma884(c.x, c.y, a1, rB[4 * ldr + rt * 8]);
+                *cp = c;
+                gmax = max(gmax, max(hi_abs(c.x), hi_abs(c.y)));
+                __syncwarp();
+                pivbad |= tile_inverse_fast(Aq + (k0 + 8) * ldw + k0 + 8, ldw, dinv + ((kt + 1) & 1) * 64, lane);
+            }
+            {
+                const int nct = 2 * n8 - ct_lo;
+                const int nch = (nct + 3) >> 2;
+                const int w0 = lookahead ? 1 : 0;
+                const int step = NW - w0;
+                if (warp >= w0) {
+                    int task = warp - w0;
+                    int ch = task / n8, rt = task - ch * n8;
+                    while (ch < nch) {
+                        const int ct0 = ct_lo + ch * 4;
+                        const double a0 = gA[rt * 8 * GLD], a1 = gA[rt * 8 * GLD + 4];
+                        double* const cp = cB + rt * 8 * ldw + ct0 * 8;
+                        const double* const bp = rB + ct0 * 8;
+                        const bool piv = (rt == kt);
+                        int q_lo = (lookahead && rt == kt + 1 && ch == 0) ? 1 : 0;
+                        const int q_hi = min(4, 2 * n8 - ct0);
+                        if (q_lo == 0 && q_hi == 4) {
+                            double2 c[4];
+                            double b0[4], b1[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                c[q] = piv ? make_double2(0.0, 0.0) : *reinterpret_cast<double2*>(cp + q * 8);
+                                b0[q] = bp[q * 8];
+                                b1[q] = bp[4 * ldr + q * 8];
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) dmma884(c[q].x, c[q].y, a0, b0[q]);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) dmma884(c[q].x, c[q].y, a1, b1[q]);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                *reinterpret_cast<double2*>(cp + q * 8) = c[q];
+                                gmax = max(gmax, max(hi_abs(c[q].x), hi_abs(c[q].y)));
+                            }
+                        } else {
+                            for (int q = q_lo; q < q_hi; ++q) {
+                                double2 c = piv ? make_double2(0.0, 0.0) : *reinterpret_cast<double2*>(cp + q * 8);
+                                dmma884(c.x, c.y, a0, bp[q * 8]);
+                                dmma884(c.x, c.y, a1, bp[4 * ldr + q * 8]);
+                                *reinterpret_cast<double2*>(cp + q * 8) = c;
+                                gmax = max(gmax, max(hi_abs(c.x), hi_abs(c.y)));
+                            }
+                        }
+                        rt += step;
+                        while (rt >= n8) {
+                            rt -= n8;
+                            ++ch;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            CEVB_PHASE(6);
+        }
+
+        // ---- squarings ------------------------------------------------------------------------
+        double* src = Bp;
+        double* dst = Aq;
+        for (int it = 0; it < s; ++it) {
+            const int nch = (n8 + 3) >> 2;
+            const int ntask = n8 * nch;
+            for (int task = warp; task < ntask; task += NW) {
+                const int ch = task / n8, rt = task - ch * n8;
+                const int ct0 = ch * 4;
+                double acc[4][2] = {};
+                const double* arow = src + (rt * 8 + g) * ldw + t4;
+                const double* bcol = src + t4 * ldw + ct0 * 8 + g;
+                for (int k4 = 0; k4 < npad; k4 += 4) {
+                    const double av = arow[k4];
+                    const double* bp = bcol + k4 * ldw;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (ct0 + q < n8) dmma884(acc[q][0], acc[q][1], av, bp[q * 8]);
+                }
+                double* drow = dst + (rt * 8 + g) * ldw + ct0 * 8 + 2 * t4;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (ct0 + q < n8)
+                        *reinterpret_cast<double2*>(drow + q * 8) = make_double2(acc[q][0], acc[q][1]);
+            }
+            __syncthreads();
+            double* tmp = src;
+            src = dst;
+            dst = tmp;
+        }
+        CEVB_PHASE(7);
+
+        // ---- floor, renormalise, NaN check, store (AR:153-159) ----------------------------------
+        int nanflag = 0;
+        for (int i = warp; i < n; i += NW) {
+            const double* xr = src + i * ldw;
+            double2 p[2];
+            double rs = 0.0;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int j = 2 * lane + 64 * pass;
+                double2 v = make_double2(0.0, 0.0);
+                if (j < ldp) {
+                    const double2 x = *reinterpret_cast<const double2*>(xr + j);
+                    v.x = (x.x != x.x) ? x.x : fmax(x.x, 1e-12);
+                    if (j + 1 < n) v.y = (x.y != x.y) ? x.y : fmax(x.y, 1e-12);
+                }
+                p[pass] = v;
+                rs += v.x + v.y;
+            }
+            rs = warp_sum(rs);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int j = 2 * lane + 64 * pass;
+                if (j < ldp) {
+                    double2 o;
+                    o.x = p[pass].x / rs;
+                    o.y = (j + 1 < n) ? p[pass].y / rs : 0.0;
+                    if (o.x != o.x || o.y != o.y) nanflag = 1;
+                    *reinterpret_cast<double2*>(Pout + (size_t)i * ldp + j) = o;
+                }
+            }
+        }
+        nanflag = __syncthreads_or(nanflag);
+        if (nanflag) {
+            for (int i = warp; i < n; i += NW)
+                for (int j = lane; j < ldp; j += 32) Pout[(size_t)i * ldp + j] = (i == j) ? 1.0 : 0.0;
+        }
+        const int g0i = block_max_int(gmax0, ish + 16);
+        const int g1i = block_max_int(gmax, ish + 16);
+        if (warp == 0 && lane == 0) {
+            int flags = nanflag ? CEVB_INFO_NAN_FALLBACK : 0;
+            // upper bound of the largest |entry| seen vs lower bound of the initial maximum
+            const double g1 = __hiloint2double(g1i, (int)0xffffffff), g0 = __hiloint2double(g0i, 0);
+            if ((g1i < 0x7ff00000 && g1 > 1.0e3 * g0) || pivbad) flags |= CEVB_INFO_GROWTH;
+            a.info[idx] = m | (s << 8) | (flags << 16);
+        }
+        __syncthreads();
+        CEVB_PHASE(8);
+    }
+    if (a.phase_clk != nullptr && tid == 0) {
+        for (int k = 0; k < 10; ++k) atomicAdd(&a.phase_clk[k], ph[k]);
+    }
+}
+
+static int fast_ldw(int npad) { return 2 * npad + 8; }
+
+static size_t fast_smem_bytes(int n) {
+    const int n8 = (n + 7) / 8, npad = n8 * 8, ldw = fast_ldw(npad), ldr = 2 * npad + 4;
+    const size_t d = (size_t)npad * ldw + (size_t)npad * GLD + 8 * (size_t)ldr + 128 + 32;
+    return d * 8 + 128;
 }
 
 static size_t branch_smem_bytes(int n, bool with_matrices) {
@@ -586,6 +1061,7 @@ static size_t branch_smem_bytes(int n, bool with_matrices) {
 }
 
 static int g_sm_count = 0;
+static unsigned long long* g_phase_clk = nullptr;
 static size_t g_smem_optin = 0;
 
 static int query_device() {
@@ -639,6 +1115,24 @@ extern "C" int cevb_expm_branches(const double* pw, const double* norms, const u
     a.full_pivot = full_pivot ? 1 : 0;
     a.use_smem = branch_smem_bytes(n, true) <= g_smem_optin ? 1 : 0;
     a.scratch_doubles = 2 * (size_t)a.npad * a.ldw;
+    a.phase_clk = g_phase_clk;
+    CEVB_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    {
+        const long long blocks = (a.M + 255) / 256;
+        order_kernel<<<(unsigned)blocks, 256, 0, st>>>(norms, t, E, a.M, info);
+        CEVB_CHECK_LAUNCH("order_kernel");
+    }
+    const int grid = cevb_expm_grid(n, a.M);
+    const bool fast = !a.full_pivot && a.npad <= 104 && fast_smem_bytes(n) <= g_smem_optin;
+    if (fast) {
+        a.ldw = fast_ldw(a.npad);
+        const size_t smem = fast_smem_bytes(n);
+        CEVB_CHECK_CUDA(cudaFuncSetAttribute(expm_branch_fast_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        expm_branch_fast_kernel<<<grid, NT, smem, st>>>(a);
+        CEVB_CHECK_LAUNCH("expm_branch_fast_kernel");
+        return 0;
+    }
     if (!a.use_smem && scratch == nullptr) {
         set_error("cevb_expm_branches: n=%d needs a global scratch buffer", n);
         return -1;
@@ -650,9 +1144,15 @@ extern "C" int cevb_expm_branches(const double* pw, const double* norms, const u
     }
     CEVB_CHECK_CUDA(cudaFuncSetAttribute(expm_branch_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CEVB_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
-    const int grid = cevb_expm_grid(n, a.M);
     expm_branch_kernel<<<grid, NT, smem, st>>>(a);
     CEVB_CHECK_LAUNCH("expm_branch_kernel");
+    return 0;
+}
+
+// Diagnostics: when set to a device buffer of 10 uint64, expm_branch_kernel accumulates SM clocks
+// spent per phase (0 order, 1 W/V build, 2 table staging, 3 U, 4 form, 5 GJ staging, 6 GJ update,
+// 7 squarings, 8 post-process + store).  nullptr switches it off.
+extern "C" int cevb_diag_set_phase_buffer(unsigned long long* buf) {
+    g_phase_clk = buf;
     return 0;
 }

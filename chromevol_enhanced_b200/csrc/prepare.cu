@@ -224,25 +224,30 @@ __global__ void __launch_bounds__(128) norms_kernel(const double* __restrict__ p
             }
         }
     } else {
+        // sparsity of Q: slot 0 = compressed columns (row indices of each column's non-zeros),
+        // slot 1 = compressed rows (column indices of each row's non-zeros); both [c][n] layouts
         const double* Q = base;
         if (tid == 0) dense_flag = 0;
         __syncthreads();
+        uint16_t* idx_c = csc + (size_t)b * 2 * CEVB_MAX_SPARSE * n;
+        uint16_t* idx_r = idx_c + (size_t)CEVB_MAX_SPARSE * n;
+        uint8_t* cnt_c = csc_cnt + (size_t)b * 2 * n;
+        uint8_t* cnt_r = cnt_c + n;
         for (int j = tid; j < n; j += blockDim.x) {
-            int cnt = 0;
+            int cc = 0, cr = 0;
             for (int i = 0; i < n; ++i) {
-                const double q = Q[(size_t)i * ldq + j];
-                if (q != 0.0) {  // NaN != 0 is true: NaN entries are kept as "non-zero"
-                    if (cnt < CEVB_MAX_SPARSE)
-                        csc[((size_t)b * CEVB_MAX_SPARSE + cnt) * n + j] = (uint16_t)i;
-                    ++cnt;
+                if (Q[(size_t)i * ldq + j] != 0.0) {  // NaN != 0 is true: kept as "non-zero"
+                    if (cc < CEVB_MAX_SPARSE) idx_c[(size_t)cc * n + j] = (uint16_t)i;
+                    ++cc;
+                }
+                if (Q[(size_t)j * ldq + i] != 0.0) {
+                    if (cr < CEVB_MAX_SPARSE) idx_r[(size_t)cr * n + j] = (uint16_t)i;
+                    ++cr;
                 }
             }
-            if (cnt > CEVB_MAX_SPARSE) {
-                csc_cnt[(size_t)b * n + j] = 255;
-                dense_flag = 1;
-            } else {
-                csc_cnt[(size_t)b * n + j] = (uint8_t)cnt;
-            }
+            cnt_c[j] = (cc > CEVB_MAX_SPARSE) ? 255 : (uint8_t)cc;
+            cnt_r[j] = (cr > CEVB_MAX_SPARSE) ? 255 : (uint8_t)cr;
+            if (cc > CEVB_MAX_SPARSE || cr > CEVB_MAX_SPARSE) dense_flag = 1;
         }
         __syncthreads();
         if (tid == 0) out[CEVB_NORM_DENSE] = dense_flag ? 1.0 : 0.0;

@@ -53,8 +53,8 @@ class ExpmWorkspace:
         self.params = torch.zeros((cap, 9), **f64)
         self.pw = torch.zeros((cap, 7, n, self.ldq), **f64)
         self.norms = torch.zeros((cap, 16), **f64)
-        self.csc = torch.zeros((cap, 12, n), dtype=torch.int16, device=device)
-        self.csc_cnt = torch.zeros((cap, n), dtype=torch.uint8, device=device)
+        self.csc = torch.zeros((cap, 2, 12, n), dtype=torch.int16, device=device)
+        self.csc_cnt = torch.zeros((cap, 2, n), dtype=torch.uint8, device=device)
         self.P = torch.empty((cap, n_t, n, self.ldp), **f64)
         self.info = torch.zeros((cap, n_t), dtype=torch.int32, device=device)
         self.counter = torch.zeros(1, dtype=torch.int32, device=device)

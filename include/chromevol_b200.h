@@ -21,8 +21,9 @@
  *                             then base_number as a double (0 = None)          (AR:44)
  *   pw      [B][7][n][ldq]    slot 0 = Q, slot k = Q^(2k), k = 1..6; ldq = cevb_ldq(n)
  *   norms   [B][16]           see CEVB_NORM_* below
- *   csc     [B][CEVB_MAX_SPARSE][n] uint16 row indices of the non-zeros of each Q column,
- *   csc_cnt [B][n]            uint8 count per column (255 = column too dense)
+ *   csc     [B][2][CEVB_MAX_SPARSE][n] uint16: slot 0 = row indices of the non-zeros of each Q
+ *                             column, slot 1 = column indices of the non-zeros of each Q row,
+ *   csc_cnt [B][2][n]         uint8 counts per column / per row (255 = too dense)
  *   t       [E]               branch lengths (>= 0; host applies AR:143-145 / AR:224-227)
  *   P       [B][E][n][ldp]    post-processed transition matrices, ldp = cevb_ldp(n)
  *   info    [B][E]            int32: Pade order m | s << 8 | flags << 16 (CEVB_INFO_*)

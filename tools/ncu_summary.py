@@ -1,0 +1,63 @@
+"""Condense ncu CSV exports into the small text summaries kept under profiles/.
+
+  python tools/ncu_summary.py launches <launches.csv>      # per-kernel share of the step
+  python tools/ncu_summary.py raw <raw.csv> [name-filter]  # key metrics of a --set full capture
+"""
+import collections
+import csv
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+    "sm__ops_path_tensor_src_fp64.sum", "sm__ops_path_tensor_src_fp64.sum.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum", "smsp__cycles_active.avg",
+]
+
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr = rows[h]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[h + 1:]:
+        if len(r) <= vi:
+            continue
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        name = r[ki].split("(")[0]
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(v[1] for v in agg.values())
+    print(f"{'kernel':55s} {'launches':>8s} {'total ms':>10s} {'share':>7s}")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{k[:55]:55s} {v[0]:8d} {v[1] / 1e6:10.3f} {100 * v[1] / tot:6.1f}%")
+
+
+def raw(path, flt=None):
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        if flt and flt not in name:
+            continue
+        print("==", name.split("(")[0])
+        for k in KEYS:
+            if k in hdr:
+                print(f"   {k:80s} {r[hdr.index(k)]:>16s} {units[hdr.index(k)]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "raw": raw}[sys.argv[1]](*sys.argv[2:])
