@@ -169,7 +169,8 @@ def workload_config(args, world):
                         f"vectors per GPU per step (rates LogUniform(1e-3,10), linear_rate U(0,0.1))",
             "per_gpu_batch": args.batch, "global_batch": args.batch * world,
             "tree_seed": TREE_SEED, "param_seed": PARAM_SEED, "parallelism": f"dp{world} (vectors sharded)",
-            "l2": "per-step working set (P: 163 MB per vector) far exceeds the 126 MB L2; no flush needed"}
+            "l2": "per-step working set (series coefficients 3.4 MB + node vectors 3.2 MB per vector, "
+                  "x batch) far exceeds the 126 MB L2; no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -282,15 +283,20 @@ def run_ours(args):
         return 0
 
     # ---- algorithmic work of the timed region
+    from chromevol_enhanced_b200 import accounting
     n = MAX_CHR + 1
-    infos = np.concatenate([x.reshape(-1) for x in info_log]) if info_log else np.zeros(0, dtype=np.int32)
-    m_arr, s_arr, fl_arr = infos & 0xff, (infos >> 8) & 0xff, infos >> 16
-    live = (fl_arr & 1) == 0
-    flops_per_step = float(np.sum((2.0 * (6 + s_arr[live]) + 8.0 / 3.0) * n ** 3))
-    expm_s = stage_ms.get("expm", 0.0) * 1e-3 / max(args.steps, 1)
-    prune_s = stage_ms.get("prune", 0.0) * 1e-3 / max(args.steps, 1)
-    prep_s = stage_ms.get("prepare", 0.0) * 1e-3 / max(args.steps, 1)
-    launches_expm = max(n_chunks, 1)
+    steps = max(args.steps, 1)
+    infos = np.concatenate([x[0].reshape(-1) for x in info_log])
+    slots = np.concatenate([x[1].reshape(-1) for x in info_log])
+    norm1 = np.concatenate([x[2] for x in info_log])
+    m_arr, s_arr = infos & 0xff, (infos >> 8) & 0xff
+    on_list = slots >= 0                                  # pairs the scaling-and-squaring kernel did
+    work = accounting.fused_work(flat, norm1)
+    t_stage = {k: v * 1e-3 / steps for k, v in stage_ms.items()}
+    apply_s, combine_s = t_stage.get("apply", 0.0), t_stage.get("combine", 0.0)
+    expm_s, prep_s, init_s = t_stage.get("expm", 0.0), t_stage.get("prepare", 0.0), t_stage.get("init", 0.0)
+    levels = int(np.count_nonzero(np.diff(flat.level_off)))
+    apply_launches = max(n_chunks * levels, 1)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -312,11 +318,19 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
-    achieved = flops_per_step / expm_s / 1e12 if expm_s > 0 else None
-    prune_bytes = flat.algorithmic_prune_bytes() * B
-    prune_gbs = prune_bytes / prune_s / 1e9 if prune_s > 0 else None
-    s_hist = {int(k): int(v) for k, v in zip(*np.unique(s_arr[live], return_counts=True))}
-    m_hist = {int(k): int(v) for k, v in zip(*np.unique(m_arr[live], return_counts=True))}
+    peak_src = "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)"
+    apply_tf = work["algorithmic_flops"] / apply_s / 1e12 if apply_s > 0 else None
+    apply_exec_tf = work["dmma_flops"] / apply_s / 1e12 if apply_s > 0 else None
+    list_flops = float(np.sum(accounting.pade_flops(n, s_arr[on_list])))
+    list_tf = list_flops / expm_s / 1e12 if (expm_s > 0 and on_list.any()) else None
+    # what the reference's algorithm (one Pade-13 expm per branch) would have cost
+    pade_equiv = float(np.sum(accounting.pade_flops(n, s_arr)))
+    pade_equiv_tf = pade_equiv / (apply_s + expm_s + prep_s) / 1e12 if apply_s > 0 else None
+    # combine kernel: reads w (or streams a materialised P) and writes the node vectors
+    combine_bytes = 8.0 * (work["fused_pairs"] * n + B * flat.n_nodes * n) + \
+        8.0 * float(on_list.sum()) * (n * n + n)
+    combine_gbs = combine_bytes / combine_s / 1e9 if combine_s > 0 else None
+    s_hist = {int(k): int(v) for k, v in zip(*np.unique(s_arr[on_list], return_counts=True))}
 
     # ---- CPU baseline (oracle port) on the host cores: bounded sample
     cpu = None
@@ -339,19 +353,31 @@ def run_ours(args):
         "e2e": {"value": total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 9 * 8),
                 "d2h_bytes_per_step": int(B * 8), "ms_per_step": t_e2e / args.steps * 1e3},
         "gpu_launches": int(args.steps * n_chunks * eng.launches_per_chunk()),
-        "roofline": {"kernel": "expm_branch_kernel", "bound": "tensor", "achieved": achieved,
+        "roofline": {"kernel": "taylor_apply_kernel", "bound": "tensor", "achieved": apply_tf,
                      "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": (achieved / fp64_peak) if achieved else None,
-                     "traffic": (traffic or {}).get("expm_branch_kernel"),
-                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
-                     "algorithmic_flops_per_launch": flops_per_step / launches_expm,
-                     "launch_ms": expm_s / launches_expm * 1e3,
-                     "pade_order_hist": m_hist, "squarings_hist": s_hist},
-        "roofline_prune": {"kernel": "prune_level_kernel", "bound": "hbm", "achieved": prune_gbs,
-                           "peak": hbm_peak, "unit": "GB/s", "frac": (prune_gbs / hbm_peak) if prune_gbs else None,
-                           "traffic": (traffic or {}).get("prune_level_kernel"), "peak_source": hbm_src,
-                           "algorithmic_bytes_per_step": prune_bytes, "ms_per_step": prune_s * 1e3},
-        "stage_ms_per_step": {"prepare": prep_s * 1e3, "expm": expm_s * 1e3, "prune": prune_s * 1e3},
+                     "frac": (apply_tf / fp64_peak) if apply_tf else None,
+                     "traffic": (traffic or {}).get("taylor_apply_kernel"),
+                     "peak_source": peak_src,
+                     "algorithmic_flops_per_launch": work["algorithmic_flops"] / apply_launches,
+                     "launch_ms": apply_s / apply_launches * 1e3,
+                     "executed_dmma_tflops": apply_exec_tf,
+                     "executed_frac": (apply_exec_tf / fp64_peak) if apply_exec_tf else None,
+                     "share_of_step": apply_s / max(sum(t_stage.values()), 1e-12),
+                     "fused_pairs": work["fused_pairs"], "mean_series_terms": work["mean_ncoef"],
+                     "note": "algorithmic = 2 n^2 terms + 3 n^2 per fused (vector, branch) pair; "
+                             "executed = DMMA flops incl. 8-branch group and 104-column padding"},
+        "roofline_squaring": {"kernel": "expm_branch_fast_kernel", "bound": "tensor",
+                              "achieved": list_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": (list_tf / fp64_peak) if list_tf else None,
+                              "pairs": int(on_list.sum()), "squarings_hist": s_hist,
+                              "note": "pairs with t||Q||_1 > 5.4; algorithmic = (2(6+s)+8/3) n^3 (SURVEY 8(d))"},
+        "roofline_combine": {"kernel": "combine_level_kernel", "bound": "hbm", "achieved": combine_gbs,
+                             "peak": hbm_peak, "unit": "GB/s",
+                             "frac": (combine_gbs / hbm_peak) if combine_gbs else None,
+                             "traffic": (traffic or {}).get("combine_level_kernel"), "peak_source": hbm_src,
+                             "algorithmic_bytes_per_step": combine_bytes},
+        "pade13_equivalent_tflops": pade_equiv_tf,
+        "stage_ms_per_step": {k: v * 1e3 for k, v in t_stage.items()},
         "single_vector": {"workload": "BASELINE configs[1]: one vector logL + argmax states",
                           "ms": t_single * 1e3, "evals_per_s": 1.0 / t_single},
         "repivot_events": eng.repivot_events,

@@ -49,6 +49,11 @@ struct BranchArgs {
     int B, E, n, ldq, ldp, n8, npad, ldw, ldr, use_smem, full_pivot;
     size_t scratch_doubles;  // per CTA
     unsigned long long* phase_clk;  // optional diagnostics: SM clocks per phase (thread 0 of each CTA)
+    // optional compact work list (cevb_expm_plan): queue position q handles matrix worklist[q]
+    // and writes P slot q; the list length is read from the device
+    const int32_t* worklist;
+    const unsigned int* work_count;
+    long long work_cap;
 };
 
 struct Order {
@@ -255,13 +260,21 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_kernel(BranchArgs a) {
             ish[0] = (int)(w & 0xffffffffu);
         }
         __syncthreads();
-        const long long idx = (long long)(unsigned)ish[0];
-        if (idx >= a.M) break;
+        const long long qpos = (long long)(unsigned)ish[0];
+        long long idx = qpos;
+        if (a.worklist != nullptr) {
+            long long lim = (long long)*a.work_count;
+            if (lim > a.work_cap) lim = a.work_cap;
+            if (qpos >= lim) break;
+            idx = a.worklist[qpos];
+        } else if (qpos >= a.M) {
+            break;
+        }
         const int b = (int)(idx / a.E), e = (int)(idx - (long long)b * a.E);
         const double tb = a.t[e];
         const double* nr = a.norms + (size_t)b * CEVB_NNORM;
         const double* pwb = a.pw + (size_t)b * CEVB_NPOW * matq;
-        double* Pout = a.P + (size_t)idx * n * a.ldp;
+        double* Pout = a.P + (size_t)qpos * n * a.ldp;
 
         const int code = a.info[idx];   // written by order_kernel: m | s << 8 | fail << 16
         const int m = code & 0xff, s = (code >> 8) & 0xff, fail = code >> 16;
@@ -705,12 +718,20 @@ __global__ void __launch_bounds__(NT, 1) expm_branch_fast_kernel(BranchArgs a) {
     for (;;) {
         if (tid == 0) ish[0] = (int)atomicAdd(a.counter, 1u);
         __syncthreads();
-        const long long idx = (long long)(unsigned)ish[0];
-        if (idx >= a.M) break;
+        const long long qpos = (long long)(unsigned)ish[0];
+        long long idx = qpos;
+        if (a.worklist != nullptr) {
+            long long lim = (long long)*a.work_count;
+            if (lim > a.work_cap) lim = a.work_cap;
+            if (qpos >= lim) break;
+            idx = a.worklist[qpos];
+        } else if (qpos >= a.M) {
+            break;
+        }
         const int b = (int)(idx / a.E), e = (int)(idx - (long long)b * a.E);
         const double tb = a.t[e];
         const double* __restrict__ pwb = a.pw + (size_t)b * CEVB_NPOW * matq;
-        double* __restrict__ Pout = a.P + (size_t)idx * n * ldp;
+        double* __restrict__ Pout = a.P + (size_t)qpos * n * ldp;
         const int code = a.info[idx];
         const int m = code & 0xff, s = (code >> 8) & 0xff, fail = code >> 16;
         CEVB_PHASE(0);
@@ -1095,10 +1116,11 @@ extern "C" int cevb_expm_grid(int n, long long n_matrices) {
     return (int)(ctas < 1 ? 1 : ctas);
 }
 
-extern "C" int cevb_expm_branches(const double* pw, const double* norms, const uint16_t* csc,
-                                  const uint8_t* csc_cnt, const double* t, int B, int E, int n,
-                                  double* P, int32_t* info, void* scratch, unsigned int* counter,
-                                  int full_pivot, void* stream) {
+static int expm_branches_impl(const double* pw, const double* norms, const uint16_t* csc,
+                              const uint8_t* csc_cnt, const double* t, int B, int E, int n,
+                              double* P, int32_t* info, void* scratch, unsigned int* counter,
+                              int full_pivot, const int32_t* worklist,
+                              const unsigned int* work_count, long long work_cap, void* stream) {
     if (B <= 0 || E <= 0) return 0;
     if (n < 2 || n > 288) {
         set_error("cevb_expm_branches: n=%d outside the supported range 2..288", n);
@@ -1116,13 +1138,14 @@ extern "C" int cevb_expm_branches(const double* pw, const double* norms, const u
     a.use_smem = branch_smem_bytes(n, true) <= g_smem_optin ? 1 : 0;
     a.scratch_doubles = 2 * (size_t)a.npad * a.ldw;
     a.phase_clk = g_phase_clk;
+    a.worklist = worklist; a.work_count = work_count; a.work_cap = work_cap;
     CEVB_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
     {
         const long long blocks = (a.M + 255) / 256;
         order_kernel<<<(unsigned)blocks, 256, 0, st>>>(norms, t, E, a.M, info);
         CEVB_CHECK_LAUNCH("order_kernel");
     }
-    const int grid = cevb_expm_grid(n, a.M);
+    const int grid = cevb_expm_grid(n, worklist ? (work_cap < a.M ? work_cap : a.M) : a.M);
     const bool fast = !a.full_pivot && a.npad <= 104 && fast_smem_bytes(n) <= g_smem_optin;
     if (fast) {
         a.ldw = fast_ldw(a.npad);
@@ -1147,6 +1170,25 @@ extern "C" int cevb_expm_branches(const double* pw, const double* norms, const u
     expm_branch_kernel<<<grid, NT, smem, st>>>(a);
     CEVB_CHECK_LAUNCH("expm_branch_kernel");
     return 0;
+}
+
+extern "C" int cevb_expm_branches(const double* pw, const double* norms, const uint16_t* csc,
+                                  const uint8_t* csc_cnt, const double* t, int B, int E, int n,
+                                  double* P, int32_t* info, void* scratch, unsigned int* counter,
+                                  int full_pivot, void* stream) {
+    return expm_branches_impl(pw, norms, csc, csc_cnt, t, B, E, n, P, info, scratch, counter,
+                              full_pivot, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int cevb_expm_branches_list(const double* pw, const double* norms, const uint16_t* csc,
+                                       const uint8_t* csc_cnt, const double* t, int B, int E, int n,
+                                       double* P, int32_t* info, void* scratch,
+                                       unsigned int* counter, int full_pivot,
+                                       const int32_t* worklist, const unsigned int* work_count,
+                                       long long work_cap, void* stream) {
+    if (worklist == nullptr || work_count == nullptr || work_cap <= 0) return 0;
+    return expm_branches_impl(pw, norms, csc, csc_cnt, t, B, E, n, P, info, scratch, counter,
+                              full_pivot, worklist, work_count, work_cap, stream);
 }
 
 // Diagnostics: when set to a device buffer of 10 uint64, expm_branch_kernel accumulates SM clocks

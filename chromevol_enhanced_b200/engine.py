@@ -5,7 +5,12 @@ This is the additive, batched entry point that sits beside the reference-shaped 
 memory and streams only); all arithmetic happens in the hand-written kernels behind the C ABI.
 
 Pipeline per chunk of parameter vectors (one stream, no host synchronisation inside):
-    cevb_build_q -> cevb_expm_prepare -> cevb_expm_branches -> cevb_prune [-> cevb_argmax_states]
+  path="fused" (default): P(t) is never written to HBM for branches with t ||Q||_1 <= 5.4
+    cevb_build_q -> cevb_expm_prepare -> cevb_taylor_prepare -> cevb_expm_plan ->
+    cevb_expm_branches_list (only the pairs that need squarings) -> cevb_prune_fused
+  path="materialised": every P(t) by Pade + scaling-and-squaring, then streamed by the pruning
+    cevb_build_q -> cevb_expm_prepare -> cevb_expm_branches -> cevb_prune
+[-> cevb_argmax_states]
 """
 from __future__ import annotations
 
@@ -20,6 +25,7 @@ from .flatten import FlatTree
 PARAM_ORDER = ['gain', 'loss', 'dupl', 'demidupl_gain', 'demidupl_loss',
                'base_number_gain', 'base_number_loss', 'linear_rate', 'base_number']
 
+FUSED_INIT, FUSED_APPLY, FUSED_COMBINE, FUSED_ALL = 1, 2, 4, 7
 INFO_IDENTITY_T0 = 1
 INFO_NAN_FALLBACK = 2
 INFO_GROWTH = 4
@@ -44,9 +50,12 @@ def _stream_ptr():
 class ExpmWorkspace:
     """Device buffers for `cap` parameter vectors x `n_t` branch lengths of order n."""
 
-    def __init__(self, n, n_t, cap, device):
+    def __init__(self, n, n_t, cap, device, p_slots=None, n_nodes=0):
+        """p_slots: number of materialised matrices P can hold (default cap * n_t, i.e. every
+        pair); n_nodes > 0 also allocates the fused path's tables."""
         lib = _lib.load()
         self.n, self.n_t, self.cap, self.device = n, n_t, cap, device
+        self.p_slots = int(cap * n_t if p_slots is None else p_slots)
         self.ldq = lib.cevb_ldq(n)
         self.ldp = lib.cevb_ldp(n)
         f64 = dict(dtype=torch.float64, device=device)
@@ -55,9 +64,19 @@ class ExpmWorkspace:
         self.norms = torch.zeros((cap, 16), **f64)
         self.csc = torch.zeros((cap, 2, 12, n), dtype=torch.int16, device=device)
         self.csc_cnt = torch.zeros((cap, 2, n), dtype=torch.uint8, device=device)
-        self.P = torch.empty((cap, n_t, n, self.ldp), **f64)
+        if p_slots is None:
+            self.P = torch.empty((cap, n_t, n, self.ldp), **f64)
+        else:
+            self.P = torch.empty((max(self.p_slots, 1), n, self.ldp), **f64)
         self.info = torch.zeros((cap, n_t), dtype=torch.int32, device=device)
         self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        if n_nodes:
+            self.tc = torch.empty((cap, lib.cevb_taylor_doubles(n)), **f64)
+            self.slot = torch.empty((cap, n_t), dtype=torch.int32, device=device)
+            self.worklist = torch.empty(max(self.p_slots, 1), dtype=torch.int32, device=device)
+            self.work_count = torch.zeros(1, dtype=torch.int32, device=device)
+            self.w = torch.zeros((cap, n_nodes, self.ldp), **f64)
+            self.mode = torch.zeros((cap, n_nodes), dtype=torch.uint8, device=device)
         scratch_bytes = lib.cevb_expm_scratch_bytes(n)
         grid = lib.cevb_expm_grid(n, cap * n_t)
         self.scratch = (torch.empty(scratch_bytes * grid // 8 + 8, **f64)
@@ -72,8 +91,12 @@ class ExpmWorkspace:
 class LikelihoodEngine:
     """Tree + data resident on the device; evaluates batches of parameter vectors."""
 
-    def __init__(self, flat: FlatTree, device=None, max_workspace_bytes=32 << 30, chunk=None):
+    def __init__(self, flat: FlatTree, device=None, max_workspace_bytes=32 << 30, chunk=None,
+                 path="fused"):
         _lib.require_device()
+        if path not in ("fused", "materialised"):
+            raise ValueError("path must be 'fused' or 'materialised'")
+        self.path = path
         self.lib = _lib.load()
         self.flat = flat
         self.device = torch.device(device if device is not None else
@@ -88,11 +111,29 @@ class LikelihoodEngine:
         self.d_leaf_code = torch.as_tensor(flat.leaf_code, **i32)
         self.d_t = torch.as_tensor(flat.t_unique, dtype=torch.float64, device=self.device)
         self.h_level_off = np.ascontiguousarray(flat.level_off, dtype=np.int32)
-        per_vec = (ExpmWorkspace.bytes_per_vector(self.n, flat.n_t)
-                   + 8 * flat.n_nodes * self.ldp)
-        if chunk is None:
-            chunk = max(1, min(4096, int(max_workspace_bytes // max(per_vec, 1))))
+        self.d_level_child = torch.as_tensor(flat.level_child, **i32)
+        self.h_level_child_off = np.ascontiguousarray(flat.level_child_off, dtype=np.int32)
+        self.d_t_node = torch.as_tensor(flat.dist_eff, dtype=torch.float64, device=self.device)
+        mat_bytes = 8 * self.n * self.ldp
+        if path == "fused":
+            # per vector: powers + series coefficients + node vectors + w; the rest of the budget
+            # holds materialised matrices (only pairs with t ||Q||_1 > 5.4 need one)
+            per_vec = (8 * 7 * self.n * self.lib.cevb_ldq(self.n)
+                       + 8 * self.lib.cevb_taylor_doubles(self.n)
+                       + 16 * flat.n_nodes * self.ldp + 16 * flat.n_t + 64 * self.n)
+            if chunk is None:
+                chunk = max(1, min(4096, int((max_workspace_bytes // 2) // max(per_vec, 1))))
+            self.p_budget = max(int(max_workspace_bytes) - int(chunk) * per_vec,
+                                flat.n_t * mat_bytes)
+        else:
+            per_vec = (ExpmWorkspace.bytes_per_vector(self.n, flat.n_t)
+                       + 8 * flat.n_nodes * self.ldp)
+            if chunk is None:
+                chunk = max(1, min(4096, int(max_workspace_bytes // max(per_vec, 1))))
+            self.p_budget = None
+        self.mat_bytes = mat_bytes
         self.chunk = int(chunk)
+        self.overflow_events = 0
         self._ws = None
         self._node_vec = None
         self._cap = 0
@@ -108,7 +149,12 @@ class LikelihoodEngine:
             return
         self._ws = None
         self._node_vec = None
-        self._ws = ExpmWorkspace(self.n, self.flat.n_t, cap, self.device)
+        if self.path == "fused":
+            slots = int(min(cap * self.flat.n_t, max(self.p_budget // self.mat_bytes, self.flat.n_t)))
+            self._ws = ExpmWorkspace(self.n, self.flat.n_t, cap, self.device, p_slots=slots,
+                                     n_nodes=self.flat.n_nodes)
+        else:
+            self._ws = ExpmWorkspace(self.n, self.flat.n_t, cap, self.device)
         f64 = dict(dtype=torch.float64, device=self.device)
         self._node_vec = torch.empty((cap, self.flat.n_nodes, self.ldp), **f64)
         self._logl = torch.empty(cap, **f64)
@@ -159,10 +205,65 @@ class LikelihoodEngine:
             _lib.ptr(self._logl), _lib.ptr(self._rescales), _stream_ptr()), "cevb_prune")
         self._mark("prune", e0)
 
+    def _fused_chunk(self, ws, nb, d_root_freq, full_pivot=0):
+        lib, st, f = self.lib, _stream_ptr(), self.flat
+        e0 = self._mark("prepare")
+        _lib.check(lib.cevb_build_q(_lib.ptr(ws.params), nb, self.n, _lib.ptr(ws.pw), st),
+                   "cevb_build_q")
+        _lib.check(lib.cevb_expm_prepare(_lib.ptr(ws.pw), nb, self.n, _lib.ptr(ws.norms),
+                                         _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt), st),
+                   "cevb_expm_prepare")
+        _lib.check(lib.cevb_taylor_prepare(_lib.ptr(ws.pw), _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt),
+                                           nb, self.n, _lib.ptr(ws.tc), st), "cevb_taylor_prepare")
+        _lib.check(lib.cevb_expm_plan(_lib.ptr(ws.norms), _lib.ptr(self.d_t), nb, f.n_t,
+                                      ws.p_slots, _lib.ptr(ws.slot), _lib.ptr(ws.worklist),
+                                      _lib.ptr(ws.work_count), st), "cevb_expm_plan")
+        e1 = self._mark("prepare", e0)
+        _lib.check(lib.cevb_expm_branches_list(
+            _lib.ptr(ws.pw), _lib.ptr(ws.norms), _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt),
+            _lib.ptr(self.d_t), nb, f.n_t, self.n, _lib.ptr(ws.P), _lib.ptr(ws.info),
+            _lib.ptr(ws.scratch), _lib.ptr(ws.counter), full_pivot, _lib.ptr(ws.worklist),
+            _lib.ptr(ws.work_count), ws.p_slots, st), "cevb_expm_branches_list")
+        e2 = self._mark("expm", e1)
+
+        def prune(lo, hi, stages):
+            _lib.check(lib.cevb_prune_fused(
+                _lib.ptr(ws.tc), _lib.ptr(ws.norms), _lib.ptr(ws.P), _lib.ptr(ws.slot), nb, f.n_t,
+                self.n, f.n_nodes, f.root, _lib.ptr(self.d_level_nodes),
+                self.h_level_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), f.n_levels,
+                _lib.ptr(self.d_child_off), _lib.ptr(self.d_child_idx), _lib.ptr(self.d_branch_of),
+                _lib.ptr(self.d_leaf_code), _lib.ptr(self.d_level_child),
+                self.h_level_child_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                _lib.ptr(self.d_t_node), _lib.ptr(d_root_freq), _lib.ptr(self._node_vec),
+                _lib.ptr(ws.w), _lib.ptr(ws.mode), _lib.ptr(self._logl), _lib.ptr(self._rescales),
+                lo, hi, stages, st), "cevb_prune_fused")
+
+        if self.stage_events is None:
+            prune(0, f.n_levels, FUSED_ALL)
+        else:
+            # same launches, issued level by level so the two kernels can be timed separately
+            prune(0, 0, FUSED_INIT)
+            ev = self._mark("init", e2)
+            for lv in range(f.n_levels):
+                prune(lv, lv + 1, FUSED_APPLY)
+                ev = self._mark("apply", ev)
+                prune(lv, lv + 1, FUSED_COMBINE)
+                ev = self._mark("combine", ev)
+
     def _run_chunk(self, d_params_chunk, d_root_freq, full_pivot=0):
         nb = d_params_chunk.shape[0]
         ws = self._ws
         ws.params[:nb].copy_(d_params_chunk)
+        if self.path == "fused":
+            self._fused_chunk(ws, nb, d_root_freq, full_pivot)
+            self._growth_flag |= ((ws.info[:nb] >> 16) & INFO_GROWTH).any()
+            self._overflow_flag |= (ws.work_count[0] > ws.p_slots)
+            self._materialised += ws.work_count[0].to(torch.int64)
+            if self.keep_info:
+                self.info_log.append((ws.info[:nb].cpu().numpy().copy(),
+                                      ws.slot[:nb].cpu().numpy().copy(),
+                                      ws.norms[:nb, 0].cpu().numpy().copy()))
+            return
         self._transition_matrices(ws, nb, full_pivot)
         # element-growth monitor of the tile-pivoted solve: OR into a device flag, no host sync
         self._growth_flag |= ((ws.info[:nb] >> 16) & INFO_GROWTH).any()
@@ -171,9 +272,12 @@ class LikelihoodEngine:
         self._prune(ws, nb, d_root_freq)
 
     def launches_per_chunk(self):
-        """Kernel launches of ours per chunk: build_q, 4 power GEMMs, norms, expm, leaf init and
-        one pruning kernel per non-empty level."""
-        return 8 + int(np.count_nonzero(np.diff(self.flat.level_off)))
+        """Kernel launches of ours per chunk.  materialised: build_q, 4 power GEMMs, norms, order,
+        expm, leaf init and one pruning kernel per non-empty level.  fused: build_q, 4 power
+        GEMMs, norms, series coefficients, plan, order, expm (work list), leaf init and two
+        kernels (apply, combine) per non-empty level."""
+        levels = int(np.count_nonzero(np.diff(self.flat.level_off)))
+        return (11 + 2 * levels) if self.path == "fused" else (9 + levels)
 
     # ------------------------------------------------------------------ public
     def log_likelihood(self, params, root_freq=None, check_growth=True):
@@ -190,19 +294,35 @@ class LikelihoodEngine:
         out = torch.empty(B, dtype=torch.float64, device=self.device)
         self.rescale_counts = torch.zeros(B, dtype=torch.int32, device=self.device)
         self._ensure(min(self.chunk, B))
-        self._growth_flag = torch.zeros((), dtype=torch.bool, device=self.device)
-        for full_pivot in (0, 1):
-            for lo in range(0, B, self._cap):
-                hi = min(B, lo + self._cap)
+        full_pivot = 0
+        step = self._cap
+        while True:
+            self._growth_flag = torch.zeros((), dtype=torch.bool, device=self.device)
+            self._overflow_flag = torch.zeros((), dtype=torch.bool, device=self.device)
+            self._materialised = torch.zeros((), dtype=torch.int64, device=self.device)
+            for lo in range(0, B, step):
+                hi = min(B, lo + step)
                 self._run_chunk(d_params[lo:hi], d_root, full_pivot)
                 out[lo:hi].copy_(self._logl[:hi - lo])
                 self.rescale_counts[lo:hi].copy_(self._rescales[:hi - lo])
-            # one host read at the end; a tripped monitor (not seen in practice) redoes the batch
-            # with full partial pivoting in every panel
-            if full_pivot or not check_growth or not bool(self._growth_flag.item()):
+            if not check_growth:
                 break
-            self.repivot_events += 1
-        self.n_chunks = (B + self._cap - 1) // self._cap
+            # one host read at the end of the batch
+            flags = torch.stack([self._growth_flag, self._overflow_flag]).cpu().numpy()
+            if flags[1]:
+                # more pairs needed a materialised matrix than P has slots: redo the batch in
+                # chunks small enough that every pair of a chunk fits
+                self.overflow_events += 1
+                step = max(1, self._ws.p_slots // max(self.flat.n_t, 1))
+                continue
+            if flags[0] and not full_pivot:
+                # a tripped element-growth monitor (not seen in practice) redoes the batch with
+                # full partial pivoting in every panel
+                self.repivot_events += 1
+                full_pivot = 1
+                continue
+            break
+        self.n_chunks = (B + step - 1) // step
         self.last_batch = B
         return out
 
@@ -211,7 +331,10 @@ class LikelihoodEngine:
         return self._node_vec[which, :, :self.n]
 
     def transition_matrices(self, which=0):
-        """(n_t, n, n) view of the P matrices of vector `which` of the last chunk."""
+        """(n_t, n, n) view of the P matrices of vector `which` of the last chunk
+        (materialised path only: the fused path does not form them)."""
+        if self.path == "fused":
+            raise _lib.CevbError("the fused path does not materialise P; use path='materialised'")
         return self._ws.P[which, :, :, :self.n]
 
     def order_info(self, which=0):

@@ -100,6 +100,20 @@ class FlatTree:
         self.level_off = level_off
         self.n_levels = n_levels
 
+        # branches grouped by the level of their PARENT (the fused kernel handles one level's
+        # branches per launch), longest first so that 8-branch groups need similar series lengths
+        lvl_child = []
+        lvl_child_off = [0]
+        for lv in range(n_levels):
+            kids = []
+            for p in self.level_nodes[level_off[lv]:level_off[lv + 1]]:
+                kids.extend(self.child_idx[child_off[p]:child_off[p + 1]].tolist())
+            kids.sort(key=lambda c: -(eff[c] if eff[c] == eff[c] else 0.0))
+            lvl_child.extend(kids)
+            lvl_child_off.append(len(lvl_child))
+        self.level_child = np.asarray(lvl_child, dtype=np.int32)
+        self.level_child_off = np.asarray(lvl_child_off, dtype=np.int32)
+
         # pre-order (parents before children, children in file order) for the simulator (AR:551)
         pre = []
         stack = [0]

@@ -44,6 +44,12 @@ extern "C" {
 #define CEVB_NNORM 16
 #define CEVB_MAX_SPARSE 12
 #define CEVB_NEVENT 8
+#define CEVB_TAYLOR_KC 10       /* chunks of 4 series coefficients kept per vector: degrees 0..39 */
+#define CEVB_FUSED_INIT 1
+#define CEVB_FUSED_APPLY 2
+#define CEVB_FUSED_COMBINE 4
+#define CEVB_FUSED_ALL 7
+#define CEVB_TAYLOR_THETA 5.4   /* t ||Q||_1 up to which expm(Q t) is summed without squaring     */
 
 /* norms[b][.] */
 #define CEVB_NORM_ONE 0      /* ||Q||_1 */
@@ -91,6 +97,61 @@ int cevb_expm_branches(const double* pw, const double* norms, const uint16_t* cs
                        const uint8_t* csc_cnt, const double* t, int B, int E, int n, double* P,
                        int32_t* info, void* scratch, unsigned int* counter, int full_pivot,
                        void* stream);
+
+/* Same, for a compact work list built by cevb_expm_plan: queue position q computes matrix
+ * worklist[q] (= b * E + e) into P slot q, for q < min(*work_count, work_cap). */
+int cevb_expm_branches_list(const double* pw, const double* norms, const uint16_t* csc,
+                            const uint8_t* csc_cnt, const double* t, int B, int E, int n, double* P,
+                            int32_t* info, void* scratch, unsigned int* counter, int full_pivot,
+                            const int32_t* worklist, const unsigned int* work_count,
+                            long long work_cap, void* stream);
+
+/* ---- (2c) fused path tables.  All branches of a parameter vector share Q (AR:230-233 with no
+ * branch_params), so expm(Q t) = sum_k t^k C_k with C_k = Q^k / k! formed once per vector:
+ *   tc [B][n][CEVB_TAYLOR_KC][n_pad][4]   (n_pad = n rounded up to 8; cevb_taylor_doubles(n)
+ *   doubles per vector); chunk c of row i holds degrees 4c..4c+3 interleaved per column.
+ * cevb_expm_plan routes every (vector, branch length) pair with t ||Q||_1 > CEVB_TAYLOR_THETA
+ * to the scaling-and-squaring kernel: slot [B][E] = position in worklist (-1 = fused path,
+ * -2 = list overflow), *count = pairs found (may exceed cap; the caller then re-plans). */
+size_t cevb_taylor_doubles(int n);
+int cevb_taylor_prepare(const double* pw, const uint16_t* csc, const uint8_t* csc_cnt, int B, int n,
+                        double* tc, void* stream);
+int cevb_expm_plan(const double* norms, const double* t, int B, int E, long long cap, int32_t* slot,
+                   int32_t* worklist, unsigned int* count, void* stream);
+
+/* ---- (2d+3) fused transition-probability x child-vector product, AR:136-166 + AR:237 without
+ * materialising P: for every listed branch (items[k] = child node id, branch length
+ * t_node[child]) and vector b,
+ *   w[b][child][i] = sum_j P'[i][j] L_child[j],  P' = post(expm(Q_b t))
+ * evaluated on the FP64 tensor cores from tc.  L_child is the one-hot / uniform leaf vector
+ * (leaf_code >= 0 / == -1) or node_vec[b][child] (leaf_code == -2).  mode [B][n_nodes] must be
+ * zero on entry; the kernel sets 1 where P is the identity (t == 0, NaN fallback) and 2 where
+ * the pair is on the materialised path -- w is not written for those. */
+int cevb_taylor_apply(const double* tc, const double* norms, int B, int n, int n_nodes,
+                      const int32_t* items, int n_items, const double* t_node,
+                      const int32_t* leaf_code, const double* node_vec, double* w, uint8_t* mode,
+                      void* stream);
+
+/* Whole tree with the fused path: same contract and tree arrays as cevb_prune, plus
+ *   level_child [n_branches]  child nodes grouped by the level of their parent (any order
+ *                             inside a level; longest branches first packs the work best),
+ *   level_child_off [n_levels+1] HOST offsets into level_child,
+ *   t_node [n_nodes]          effective branch length above every node,
+ *   P / slot                  materialised matrices and slot map from cevb_expm_plan +
+ *                             cevb_expm_branches_list (E = row length of slot),
+ *   w [B][n_nodes][ldp], mode [B][n_nodes]   scratch.
+ * Levels [level_begin, level_end) are processed; `stages` is a mask of CEVB_FUSED_INIT (zero
+ * mode / rescales, write the leaf vectors), CEVB_FUSED_APPLY and CEVB_FUSED_COMBINE.  The whole
+ * tree in one call is (0, n_levels, CEVB_FUSED_ALL); the split form lets a caller time the two
+ * kernels of a level separately. */
+int cevb_prune_fused(const double* tc, const double* norms, const double* P, const int32_t* slot,
+                     int B, int E, int n, int n_nodes, int root, const int32_t* level_nodes,
+                     const int32_t* level_off_host, int n_levels, const int32_t* child_off,
+                     const int32_t* child_idx, const int32_t* branch_of, const int32_t* leaf_code,
+                     const int32_t* level_child, const int32_t* level_child_off_host,
+                     const double* t_node, const double* root_freq, double* node_vec, double* w,
+                     uint8_t* mode, double* logl, int32_t* rescales, int level_begin, int level_end,
+                     int stages, void* stream);
 
 /* ---- (3) Felsenstein pruning: replaces ChromEvolLikelihoodCalculator.
  * calculate_likelihood_at_node / calculate_total_log_likelihood, AR:189-272.

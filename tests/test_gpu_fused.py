@@ -1,0 +1,208 @@
+"""GPU parity tests of the fused path (series coefficients + tensor-core apply kernel), called
+through the C ABI, against the CPU oracle.
+
+The apply kernel never writes P, so P parity is checked through its action on one-hot child
+vectors: w for a child observed in state j is column j of the post-processed P (AR:153-154),
+which is compared entry by entry (1e-12 absolute, north_star) with the oracle's P.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import chromevol_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _apply(rows, times, N, child_vectors=None, codes=None):
+    """w[b, e, k, :] for every (vector b, time e, child k); children are one-hot columns 0..n-1
+    unless `child_vectors` (K, n) / `codes` (K,) are given.  Returns (w, mode)."""
+    import torch
+    from chromevol_enhanced_b200 import _lib
+    from chromevol_enhanced_b200.engine import ExpmWorkspace, _stream_ptr
+    _lib.require_device()
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    n = N + 1
+    rows = np.atleast_2d(np.asarray(rows, dtype=np.float64))
+    times = np.asarray(times, dtype=np.float64)
+    B, E = rows.shape[0], times.shape[0]
+    if codes is None:
+        codes = np.arange(n) if child_vectors is None else np.full(child_vectors.shape[0], -2)
+    codes = np.asarray(codes, dtype=np.int32)
+    K = codes.shape[0]
+    n_nodes = E * K
+    ws = ExpmWorkspace(n, E, B, dev)
+    ws.params.copy_(torch.as_tensor(rows, device=dev))
+    st = _stream_ptr()
+    _lib.check(lib.cevb_build_q(_lib.ptr(ws.params), B, n, _lib.ptr(ws.pw), st), "build_q")
+    _lib.check(lib.cevb_expm_prepare(_lib.ptr(ws.pw), B, n, _lib.ptr(ws.norms), _lib.ptr(ws.csc),
+                                     _lib.ptr(ws.csc_cnt), st), "prepare")
+    tc = torch.empty((B, lib.cevb_taylor_doubles(n)), dtype=torch.float64, device=dev)
+    _lib.check(lib.cevb_taylor_prepare(_lib.ptr(ws.pw), _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt), B, n,
+                                       _lib.ptr(tc), st), "taylor_prepare")
+    ldp = ws.ldp
+    t_node = torch.as_tensor(np.repeat(times, K), device=dev)
+    leaf_code = torch.as_tensor(np.tile(codes, E), device=dev)
+    node_vec = torch.zeros((B, n_nodes, ldp), dtype=torch.float64, device=dev)
+    if child_vectors is not None:
+        cv = torch.as_tensor(np.asarray(child_vectors, dtype=np.float64), device=dev)
+        node_vec[:, :, :n] = cv.repeat(E, 1)[None]
+    items = torch.arange(n_nodes, dtype=torch.int32, device=dev)
+    w = torch.full((B, n_nodes, ldp), float("nan"), dtype=torch.float64, device=dev)
+    mode = torch.zeros((B, n_nodes), dtype=torch.uint8, device=dev)
+    _lib.check(lib.cevb_taylor_apply(_lib.ptr(tc), _lib.ptr(ws.norms), B, n, n_nodes, _lib.ptr(items),
+                                     n_nodes, _lib.ptr(t_node), _lib.ptr(leaf_code), _lib.ptr(node_vec),
+                                     _lib.ptr(w), _lib.ptr(mode), st), "taylor_apply")
+    torch.cuda.synchronize()
+    return (w[:, :, :n].cpu().numpy().reshape(B, E, K, n), mode.cpu().numpy().reshape(B, E, K),
+            ws.norms[:, 0].cpu().numpy())
+
+
+@pytest.mark.parametrize("N", [35, 100])
+def test_fused_p_columns_match_oracle(N):
+    """Column j of post(expm(Q t)) through the apply kernel, config-3 parameter distribution."""
+    from chromevol_enhanced_b200 import synthetic
+    rows = synthetic.random_param_rows(12, seed=4, linear='positive')
+    rows[::3, 8] = 7
+    times = np.concatenate([[0.0, 1e-6], 1e-4 + np.random.default_rng(1).exponential(0.05, 5), [0.758285]])
+    w, mode, norm1 = _apply(rows, times, N)
+    n_fused = 0
+    for b in range(rows.shape[0]):
+        Q = O.build_q(synthetic.row_to_dict(rows[b]), N)
+        assert norm1[b] == pytest.approx(np.abs(Q).sum(axis=0).max(), rel=1e-14)
+        for e, t in enumerate(times):
+            eta = t * norm1[b]
+            if t == 0.0:
+                assert (mode[b, e] == 1).all()          # identity, AR:146-148
+            elif eta > 5.4:
+                assert (mode[b, e] == 2).all()          # routed to the scaling-and-squaring kernel
+            else:
+                assert (mode[b, e] == 0).all()
+                P = w[b, e].T                           # w[k] = column k of P
+                ref = O.transition_probabilities(Q, t)
+                assert np.abs(P - ref).max() <= 1e-12, (b, t, eta)
+                n_fused += 1
+    assert n_fused > 40
+
+
+def test_fused_p_eta_sweep_up_to_theta():
+    """Series length selection: eta = t ||Q||_1 swept from 1e-6 to the 5.4 switch-over."""
+    from chromevol_enhanced_b200 import synthetic
+    row = synthetic.default_param_row()
+    row[:5] = [2.0, 1.5, 0.7, 0.4, 0.3]
+    Q = O.build_q(synthetic.row_to_dict(row), 100)
+    norm1 = np.abs(Q).sum(axis=0).max()
+    etas = np.array([1e-6, 1e-3, 0.05, 0.3, 0.9, 1.7, 2.5, 3.3, 4.1, 4.9, 5.39])
+    times = etas / norm1
+    w, mode, _ = _apply(row, times, 100)
+    for e, t in enumerate(times):
+        assert (mode[0, e] == 0).all()
+        ref = O.transition_probabilities(Q, t)
+        assert np.abs(w[0, e].T - ref).max() <= 1e-12, etas[e]
+
+
+def test_fused_non_generator_q():
+    """linear_rate < 0 gives negative off-diagonal 'rates' (SURVEY.md 7.2-2): entries of the raw
+    exponential exceed 1, so the tolerance scales with max|raw| as for the Pade path."""
+    from chromevol_enhanced_b200 import synthetic
+    rows = synthetic.random_param_rows(10, seed=9, linear='mixed')
+    times = np.array([0.003, 0.02, 0.05])
+    w, mode, norm1 = _apply(rows, times, 100)
+    checked = 0
+    for b in range(rows.shape[0]):
+        Q = O.build_q(synthetic.row_to_dict(rows[b]), 100)
+        for e, t in enumerate(times):
+            if mode[b, e, 0] != 0:
+                continue
+            raw = O.raw_expm(Q, t)
+            scale = max(1.0, np.abs(raw).max())
+            ref = O.transition_probabilities(Q, t)
+            assert np.abs(w[b, e].T - ref).max() <= 1e-12 * scale
+            checked += 1
+    assert checked > 10
+
+
+def test_fused_child_vector_kinds_and_ragged_groups():
+    """Internal (dense vector), missing-data (uniform) and observed children in one launch, with
+    a branch count that is not a multiple of the 8-branch MMA group."""
+    from chromevol_enhanced_b200 import synthetic
+    rng = np.random.default_rng(3)
+    N = 100
+    rows = synthetic.random_param_rows(3, seed=11, linear='positive')
+    rows[:, :5] *= 0.2
+    times = np.array([0.01, 0.07, 0.2])
+    K = 11
+    vecs = rng.random((K, N + 1)) * 10.0 ** rng.integers(-30, 1, size=(K, 1))
+    codes = np.array([-2, -2, -1, 5, -2, 100, -2, -1, 0, -2, 37], dtype=np.int32)
+    w, mode, norm1 = _apply(rows, times, N, child_vectors=vecs, codes=codes)
+    for b in range(rows.shape[0]):
+        Q = O.build_q(synthetic.row_to_dict(rows[b]), N)
+        for e, t in enumerate(times):
+            if t * norm1[b] > 5.4:
+                continue
+            P = O.transition_probabilities(Q, t)
+            for k in range(K):
+                L = vecs[k] if codes[k] == -2 else (np.full(N + 1, 1.0 / (N + 1)) if codes[k] == -1
+                                                    else O.leaf_vector(int(codes[k]), N))
+                ref = P @ L
+                assert np.allclose(w[b, e, k], ref, rtol=1e-11, atol=1e-12 * np.abs(L).max())
+
+
+@pytest.mark.parametrize("N", [7, 40, 103, 104, 120, 256])
+def test_fused_odd_sizes(N):
+    """Padding columns, multi-pass rows (n > 104) and the one-group-per-warp variant (n = 257)."""
+    from chromevol_enhanced_b200 import synthetic
+    rows = np.stack([synthetic.default_param_row(), synthetic.default_param_row(base_number=3)])
+    rows[1, :5] = [0.8, 0.6, 0.3, 0.1, 0.05]
+    times = np.array([0.004, 0.11, 0.6])
+    w, mode, norm1 = _apply(rows, times, N)
+    for b in range(2):
+        Q = O.build_q(synthetic.row_to_dict(rows[b]), N)
+        for e, t in enumerate(times):
+            if mode[b, e, 0] == 2:
+                continue
+            ref = O.transition_probabilities(Q, t)
+            assert np.abs(w[b, e].T - ref).max() <= 1e-12, (N, b, t)
+
+
+def test_fused_and_materialised_paths_agree_on_config3_batch():
+    """1,000 taxa / N=100, 16 vectors of the bench distribution: both device paths against each
+    other (1e-11 relative) and three of them against the oracle (1e-9 relative)."""
+    from chromevol_enhanced_b200 import synthetic
+    from chromevol_enhanced_b200.engine import LikelihoodEngine
+    from chromevol_enhanced_b200.flatten import FlatTree
+    tree = synthetic.random_tree(1000, seed=1)
+    counts = synthetic.simulate_tip_counts(tree, 100, seed=2)
+    rows = synthetic.random_param_rows(16, seed=4, linear='positive')
+    flat = FlatTree(tree, counts, 100)
+    fused = LikelihoodEngine(flat, path="fused")
+    mat = LikelihoodEngine(flat, path="materialised", max_workspace_bytes=8 << 30)
+    a = fused.log_likelihood(rows).cpu().numpy()
+    b = mat.log_likelihood(rows).cpu().numpy()
+    assert np.allclose(a, b, rtol=1e-11, atol=0)
+    assert np.array_equal(fused.rescale_counts.cpu().numpy(), mat.rescale_counts.cpu().numpy())
+    for k in (0, 5, 11):
+        ref, _, resc = O.log_likelihood(tree, counts, 100, synthetic.row_to_dict(rows[k]))
+        assert a[k] == pytest.approx(ref, rel=1e-9)
+
+
+def test_fused_worklist_overflow_is_redone():
+    """More (vector, branch) pairs need squarings than the P buffer has slots: the batch is
+    re-run in smaller chunks and still matches the materialised path."""
+    from chromevol_enhanced_b200 import synthetic
+    from chromevol_enhanced_b200.engine import LikelihoodEngine
+    from chromevol_enhanced_b200.flatten import FlatTree
+    tree = synthetic.random_tree(80, seed=12, mean_len=0.3)
+    counts = synthetic.simulate_tip_counts(tree, 40, seed=13)
+    rows = synthetic.random_param_rows(12, seed=14, linear='positive')
+    rows[:, :5] *= 3.0
+    flat = FlatTree(tree, counts, 40)
+    # workspace so small that only one vector's worth of matrices fits
+    fused = LikelihoodEngine(flat, path="fused", chunk=6, max_workspace_bytes=1 << 20)
+    mat = LikelihoodEngine(flat, path="materialised")
+    a = fused.log_likelihood(rows).cpu().numpy()
+    b = mat.log_likelihood(rows).cpu().numpy()
+    assert fused.overflow_events >= 1
+    assert np.allclose(a, b, rtol=1e-11, atol=0)

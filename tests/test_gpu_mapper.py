@@ -74,9 +74,14 @@ def test_count_distribution_against_oracle_simulator():
             keep = p * Rc >= 5
             if keep.sum() < 2:
                 continue
-            # lump the rest
+            # lump the rest; a chi-square cell needs an expectation of about 5, so a smaller
+            # remainder is merged into the last kept cell instead of standing alone
             exp = np.append(p[keep], 1 - p[keep].sum()) * Rc
             obs = np.append(h_cpu[keep], Rc - h_cpu[keep].sum())
+            if exp[-1] < 5.0:
+                exp[-2] += exp[-1]
+                obs[-2] += obs[-1]
+                exp, obs = exp[:-1], obs[:-1]
             good = exp > 1e-9
             chi2 = float(np.sum((obs[good] - exp[good]) ** 2 / exp[good]))
             dof = int(good.sum()) - 1

@@ -159,14 +159,18 @@ def _engine(tree, counts, N, **kw):
 KATS = ["kat1_default_N35", "kat2_N60_root24", "kat3_opt_full_N35", "kat4_gainloss_N35", "kat5_bn7_N35"]
 
 
+PATHS = ["fused", "materialised"]
+
+
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("name", KATS)
-def test_shipped_kats_logl_vectors_states(golden, shipped, name):
+def test_shipped_kats_logl_vectors_states(golden, shipped, name, path):
     arrays, meta = golden
     newick, counts = shipped
     kat = meta["kat"][name]
     N = kat["max_chr"]
     tree = make_tree(newick)
-    eng, flat = _engine(tree, counts, N)
+    eng, flat = _engine(tree, counts, N, path=path)
     freq = None
     if kat["root_state"] is not None:
         freq = np.zeros(N + 1)
@@ -182,13 +186,14 @@ def test_shipped_kats_logl_vectors_states(golden, shipped, name):
     assert int(eng.rescale_counts[0]) == 0
 
 
-def test_four_taxa_and_edge_cases(golden):
+@pytest.mark.parametrize("path", PATHS)
+def test_four_taxa_and_edge_cases(golden, path):
     arrays, meta = golden
     for key, vec_key, cnt_key in (("kat6_four_taxa", "kat6_vectors", "kat6_ml_count"),
                                   ("edge_polytomy", "edge_vectors", "edge_ml_count")):
         kat = meta["kat"][key]
         tree = make_tree(kat["newick"])
-        eng, flat = _engine(tree, kat["counts"], kat["max_chr"])
+        eng, flat = _engine(tree, kat["counts"], kat["max_chr"], path=path)
         ll = eng.log_likelihood(_row(O.default_params(**(kat.get("params") or {})))[None])
         assert float(ll[0]) == pytest.approx(kat["logL"], rel=1e-9)
         V = eng.node_vectors(0).cpu().numpy()
@@ -196,19 +201,21 @@ def test_four_taxa_and_edge_cases(golden):
         assert eng.ancestral_states(0)[0].cpu().numpy().tolist() == arrays[cnt_key].tolist()
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("tag", ["default", "opt_full"])
-def test_synthetic_200_taxa_golden(golden, tag):
+def test_synthetic_200_taxa_golden(golden, tag, path):
     arrays, meta = golden
     kat = meta["kat"][f"synth200_{tag}"]
     tree = make_tree(kat["newick"])
-    eng, flat = _engine(tree, kat["counts"], 60)
+    eng, flat = _engine(tree, kat["counts"], 60, path=path)
     ll = eng.log_likelihood(_row(O.default_params(**(kat["params"] or {})))[None])
     assert float(ll[0]) == pytest.approx(kat["logL"], rel=1e-9)
     assert eng.ancestral_states(0)[0].cpu().numpy().tolist() == arrays[f"synth200_{tag}_ml_count"].tolist()
     assert np.allclose(eng.node_vectors(0)[0].cpu().numpy(), arrays[f"synth200_{tag}_root_vector"], rtol=1e-9, atol=0)
 
 
-def test_batch_vs_oracle_live_and_chunking():
+@pytest.mark.parametrize("path", PATHS)
+def test_batch_vs_oracle_live_and_chunking(path):
     """A batch of parameter vectors (incl. non-generator ones) on a seeded tree against the
     oracle, evaluated once in one chunk and once in ragged chunks of 3."""
     from chromevol_enhanced_b200 import synthetic
@@ -218,9 +225,9 @@ def test_batch_vs_oracle_live_and_chunking():
     counts["t4"] = 77                      # one out-of-range count
     rows = synthetic.random_param_rows(10, seed=8, linear='mixed')
     rows[4, 8] = 5
-    eng, flat = _engine(tree, counts, 40)
+    eng, flat = _engine(tree, counts, 40, path=path)
     ll = eng.log_likelihood(rows).cpu().numpy()
-    eng3, _ = _engine(tree, counts, 40, chunk=3)
+    eng3, _ = _engine(tree, counts, 40, chunk=3, path=path)
     ll3 = eng3.log_likelihood(rows).cpu().numpy()
     assert np.array_equal(ll, ll3)
     for b in range(rows.shape[0]):
@@ -229,14 +236,15 @@ def test_batch_vs_oracle_live_and_chunking():
         assert int(eng.rescale_counts[b]) == resc
 
 
-def test_rescale_branch_is_reproduced():
+@pytest.mark.parametrize("path", PATHS)
+def test_rescale_branch_is_reproduced(path):
     """Large divergent tree: the AR:242 rescale (0 < sum < 1e-100, factor dropped) must fire on
     the same nodes as in the oracle, otherwise logL differs by hundreds."""
     from chromevol_enhanced_b200 import synthetic
     tree = synthetic.random_tree(400, seed=31, mean_len=0.4)
     counts = synthetic.simulate_tip_counts(tree, 60, seed=32, params=dict(gain=1.0, loss=1.0))
     row = synthetic.default_param_row()
-    eng, flat = _engine(tree, counts, 60)
+    eng, flat = _engine(tree, counts, 60, path=path)
     ll = float(eng.log_likelihood(row[None])[0])
     ref, _, resc = O.log_likelihood(tree, counts, 60, synthetic.row_to_dict(row))
     assert resc > 0
@@ -244,13 +252,14 @@ def test_rescale_branch_is_reproduced():
     assert ll == pytest.approx(ref, rel=1e-9)
 
 
-def test_thousand_taxa_n100_single_vector():
+@pytest.mark.parametrize("path", PATHS)
+def test_thousand_taxa_n100_single_vector(path):
     """BASELINE config 2 at full size, against the oracle (about 2 s of CPU)."""
     from chromevol_enhanced_b200 import synthetic
     tree = synthetic.random_tree(1000, seed=1)
     counts = synthetic.simulate_tip_counts(tree, 100, seed=2)
     row = synthetic.default_param_row()
-    eng, flat = _engine(tree, counts, 100)
+    eng, flat = _engine(tree, counts, 100, path=path)
     ll = float(eng.log_likelihood(row[None])[0])
     ref, vectors, resc = O.log_likelihood(tree, counts, 100, synthetic.row_to_dict(row))
     assert ll == pytest.approx(ref, rel=1e-9)
