@@ -37,16 +37,20 @@ _PROTOTYPES = {
                                            _c.c_int, c_dp, c_dp, c_dp, c_dp, _c.c_int, c_dp, c_dp,
                                            _c.c_longlong, _c.c_void_p]),
     "cevb_taylor_doubles": (_c.c_size_t, [_c.c_int]),
-    "cevb_taylor_prepare": (_c.c_int, [c_dp, c_dp, c_dp, _c.c_int, _c.c_int, c_dp, _c.c_void_p]),
+    "cevb_taylor_matrices_supported": (_c.c_int, [_c.c_int]),
+    "cevb_taylor_prepare": (_c.c_int, [c_dp, _c.c_int, _c.c_int, c_dp, c_dp, c_dp, c_dp,
+                                       _c.c_void_p]),
     "cevb_expm_plan": (_c.c_int, [c_dp, c_dp, _c.c_int, _c.c_int, _c.c_longlong, c_dp, c_dp, c_dp,
-                                  _c.c_void_p]),
-    "cevb_taylor_apply": (_c.c_int, [c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, c_dp, _c.c_int, c_dp,
-                                     c_dp, c_dp, c_dp, c_dp, _c.c_void_p]),
+                                  c_dp, _c.c_void_p]),
+    "cevb_taylor_matrices": (_c.c_int, [c_dp, c_dp, c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, c_dp,
+                                        c_dp, c_dp, _c.c_longlong, c_dp, c_dp, c_dp, _c.c_void_p]),
+    "cevb_taylor_apply": (_c.c_int, [c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, c_dp, _c.c_int,
+                                     _c.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, _c.c_void_p]),
     "cevb_prune_fused": (_c.c_int, [c_dp, c_dp, c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                     _c.c_int, c_dp, _c.POINTER(_c.c_int32), _c.c_int, c_dp, c_dp,
-                                    c_dp, c_dp, c_dp, _c.POINTER(_c.c_int32), c_dp, c_dp, c_dp,
-                                    c_dp, c_dp, c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int,
-                                    _c.c_void_p]),
+                                    c_dp, c_dp, c_dp, _c.POINTER(_c.c_int32),
+                                    _c.POINTER(_c.c_int32), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                    c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     "cevb_prune": (_c.c_int, [c_dp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, c_dp,
                               _c.POINTER(_c.c_int32), _c.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                               c_dp, c_dp, _c.c_void_p]),

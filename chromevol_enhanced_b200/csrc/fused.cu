@@ -22,6 +22,8 @@
 // that the truncation bound eta^(K+1)/(K+1)! / (1 - eta/(K+2)) is below 1e-18.
 // Branches with eta > 5.4 need squarings and therefore a materialised matrix: they are routed
 // (cevb_expm_plan) to the Pade kernel of expm.cu, whose P the combine kernel reads.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cevb {
@@ -29,7 +31,6 @@ namespace cevb {
 constexpr int F_KC = CEVB_TAYLOR_KC;       // chunks of 4 series coefficients (degrees 0..39)
 constexpr int F_JT = 13;                   // 8-column tiles per pass (104 columns)
 constexpr double F_THETA = CEVB_TAYLOR_THETA;
-constexpr int F_MAXW = 8;                  // warps per CTA of the apply kernel
 
 // number of series coefficients (degree + 1) needed for eta = t ||Q||_1
 __host__ __device__ inline int taylor_ncoef(double eta) {
@@ -41,6 +42,56 @@ __host__ __device__ inline int taylor_ncoef(double eta) {
         if ((double)(k + 2) > eta && term / (1.0 - eta / (double)(k + 2)) <= 1e-18) break;
     }
     return k + 1;
+}
+
+// squarings for eta > theta: smallest s with eta 2^-s <= theta (non-finite eta -> 0; the series
+// is then evaluated at NaN and the post-processing falls back to the identity, AR:156-159)
+__host__ __device__ inline int taylor_squarings(double eta) {
+    int s = 0;
+    while (eta > F_THETA && eta < INFINITY && s < 1000) {
+        eta *= 0.5;
+        ++s;
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ||Q||_1 and the compressed column structure of Q (row indices of the non-zeros of every
+// column), one CTA per parameter vector, one thread per column.
+__global__ void __launch_bounds__(128) q_structure_kernel(const double* __restrict__ pw, int n,
+                                                          int ldq, double* __restrict__ norms,
+                                                          uint16_t* __restrict__ csc,
+                                                          uint8_t* __restrict__ csc_cnt) {
+    __shared__ double red[4];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const double* Q = pw + (size_t)b * CEVB_NPOW * n * ldq;
+    uint16_t* idx_c = csc + (size_t)b * 2 * CEVB_MAX_SPARSE * n;
+    uint8_t* cnt_c = csc_cnt + (size_t)b * 2 * n;
+    double best = 0.0;
+    bool nan = false;
+    for (int j = tid; j < n; j += 128) {
+        int cc = 0;
+        double sum = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double q = Q[(size_t)i * ldq + j];
+            if (q != 0.0) {  // NaN != 0 is true: kept as "non-zero"
+                if (cc < CEVB_MAX_SPARSE) idx_c[(size_t)cc * n + j] = (uint16_t)i;
+                ++cc;
+            }
+            sum += fabs(q);
+        }
+        cnt_c[j] = (cc > CEVB_MAX_SPARSE) ? 255 : (uint8_t)cc;
+        if (sum != sum) nan = true;
+        best = fmax(best, sum);
+    }
+    best = warp_max(best);
+    const bool anynan = __syncthreads_or(nan);
+    if ((tid & 31) == 0) red[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+        const double m = fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
+        norms[(size_t)b * CEVB_NNORM + CEVB_NORM_ONE] = anynan ? NAN : m;   // numpy max propagates NaN
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -101,6 +152,7 @@ __global__ void __launch_bounds__(256) expm_plan_kernel(const double* __restrict
                                                         long long M, long long cap,
                                                         int32_t* __restrict__ slot,
                                                         int32_t* __restrict__ worklist,
+                                                        int32_t* __restrict__ work_s,
                                                         unsigned int* __restrict__ count) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M) return;
@@ -112,6 +164,7 @@ __global__ void __launch_bounds__(256) expm_plan_kernel(const double* __restrict
         const unsigned int q = atomicAdd(count, 1u);
         if ((long long)q < cap) {
             worklist[q] = (int32_t)idx;
+            if (work_s != nullptr) work_s[q] = taylor_squarings(eta);
             s = (int)q;
         } else {
             s = -2;  // overflow: the host sees count > cap and re-runs with smaller chunks
@@ -157,32 +210,57 @@ struct ApplyArgs {
     const double* t_node;     // [n_nodes] effective branch length above a node
     const int32_t* leaf_code; // [n_nodes]
     const double* node_vec;   // [B][n_nodes][ldp]
-    double* w;                // [B][n_nodes][ldp]
+    double* w;                // [B][n_nodes][ldp]  numerators  sum_j P'[i][j] L[j]
+    double* wr;               // [B][n_nodes][ldp]  row sums of the floored P (AR:154 divides)
     uint8_t* mode;            // [B][n_nodes]: only non-zero values are ever written
     int n_items, n, npad, ldp, ldl, n_nodes, rows_per_cta;
+    int stage_doubles_cap;    // doubles available for the coefficient ring
+    // EVAL mode: items index the branch-length array t_node [E]; the raw series value at
+    // t 2^-s goes to X[slot[b * E + item]] (n rows of ldp doubles) for the squaring kernel
+    const int32_t* slot;
+    double* X;
+    int E;
 };
 
-__host__ __device__ inline size_t apply_header_bytes(int eb) {
-    return (size_t)((16 + 4 * (3 * eb + 4) + 127) / 128) * 128;
+constexpr int APPLY_GENERAL = 0, APPLY_LEAF = 1, APPLY_EVAL = 2;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__host__ __device__ inline size_t apply_smem_bytes(int nwarps, int G, int ldl) {
-    const int eb = nwarps * G * 8;
-    return apply_header_bytes(eb) +
-           sizeof(double) * ((size_t)(eb / 8) * F_KC * 32 + (size_t)eb * ldl +
-                             2 * (size_t)F_KC * F_JT * 32);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+constexpr int F_MAXSTAGE = 4;
+
+__host__ __device__ inline size_t apply_header_bytes(int eb) {
+    return (size_t)((16 * F_MAXSTAGE + 4 * (3 * eb + 4) + 127) / 128) * 128;
+}
+// shared memory of the apply kernel: header (barriers, per-branch ints), the t^k table A
+// [eb/8][F_KC][32], the child vectors L [eb][ldl] and the ring of coefficient row tiles
+__host__ __device__ inline size_t apply_fixed_bytes(int eb, int ldl) {  // ldl = 0: no child vectors
+    return apply_header_bytes(eb) + sizeof(double) * ((size_t)(eb / 8) * F_KC * 32 + (size_t)eb * ldl);
 }
 
 // One CTA: vector b = blockIdx.z, branches [blockIdx.x * EB, +EB) of the launch's item list
-// (EB = warps * G * 8), rows [blockIdx.y * rows_per_cta, +rows_per_cta) of every P.  All warps
-// work on the same row at a time and share its coefficient tile; a warp owns G groups of 8
-// branches and keeps the G x 13 accumulator tiles of the row in registers.
-template <int G>
-__global__ void __launch_bounds__(32 * F_MAXW) taylor_apply_kernel(ApplyArgs a) {
+// (EB = NW * G * 8), rows [blockIdx.y * rows_per_cta, +rows_per_cta) of every P.  NW consumer
+// warps each own G groups of 8 branches and keep the G x 13 accumulator tiles of the current
+// row in registers; one extra producer warp streams the coefficient rows (the same tile for
+// all consumers) through a ring of shared-memory stages with full/empty mbarriers, so the
+// consumers drift apart and one warp's epilogue overlaps another warp's DMMAs.
+// MODE APPLY_LEAF: every child of the launch is an observed leaf (one-hot L): the dot product
+// is a select of one accumulator and no child vectors are staged.  MODE APPLY_EVAL: no
+// epilogue arithmetic at all -- the series value at the scaled time t 2^-s of every pair with
+// t ||Q||_1 > theta is written out for the squaring kernel.
+template <int G, int NW, int MODE>
+__global__ void __launch_bounds__(32 * (NW + 1)) taylor_apply_kernel(ApplyArgs a) {
+    constexpr bool LEAF = MODE != APPLY_GENERAL;   // no child vectors in shared memory
+    constexpr bool EVAL = MODE == APPLY_EVAL;
     extern __shared__ __align__(128) unsigned char smraw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
-    const int nwarps = blockDim.x >> 5;
-    const int EB = nwarps * G * 8;
+    constexpr int EB = NW * G * 8;
     const int b = blockIdx.z;
     const int e0 = blockIdx.x * EB;
     const int n = a.n, npad = a.npad, ldl = a.ldl;
@@ -190,19 +268,37 @@ __global__ void __launch_bounds__(32 * F_MAXW) taylor_apply_kernel(ApplyArgs a) 
     const int i_end = min(n, i_begin + a.rows_per_cta);
 
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw);
-    int* s_child = reinterpret_cast<int*>(smraw + 16);
+    uint64_t* empty = full + F_MAXSTAGE;
+    int* s_child = reinterpret_cast<int*>(smraw + 16 * F_MAXSTAGE);
     int* s_code = s_child + EB;
     int* s_nc = s_code + EB;
     double* As = reinterpret_cast<double*>(smraw + apply_header_bytes(EB));  // [EB/8][F_KC][32]
-    double* Ls = As + (size_t)(EB / 8) * F_KC * 32;                           // [EB][ldl]
-    double* Bs = Ls + (size_t)EB * ldl;                                       // [2][F_KC][F_JT*32]
+    double* Ls = As + (size_t)(EB / 8) * F_KC * 32;                           // [EB][ldl] (not LEAF)
+    double* Bs = Ls + (LEAF ? 0 : (size_t)EB * ldl);                          // ring of row tiles
 
     const double norm1 = a.norms[(size_t)b * CEVB_NNORM + CEVB_NORM_ONE];
     for (int x = tid; x < EB; x += blockDim.x) {
         const int e = e0 + x;
         int nc = 0, child = -1, code = -2;
         double tau = 0.0;
-        if (e < a.n_items) {
+        if (e < a.n_items && EVAL) {
+            const int item = a.items[e];
+            const double t = a.t_node[item];
+            const double eta = t * norm1;
+            if (t > 0.0 && !(eta <= F_THETA)) {
+                child = a.slot[(size_t)b * a.E + item];     // P slot of this pair (< 0: overflow)
+                if (child >= 0) {
+                    const int sq = taylor_squarings(eta);
+                    if (eta < INFINITY) {
+                        tau = ldexp(t, -sq);
+                        nc = taylor_ncoef(ldexp(eta, -sq));
+                    } else {
+                        tau = NAN;   // NaN / inf rates: NaN series, identity after post-processing
+                        nc = 4;
+                    }
+                }
+            }
+        } else if (e < a.n_items) {
             child = a.items[e];
             code = a.leaf_code[child];
             const double t = a.t_node[child];
@@ -210,7 +306,7 @@ __global__ void __launch_bounds__(32 * F_MAXW) taylor_apply_kernel(ApplyArgs a) 
             if (!(t > 0.0)) {
                 a.mode[(size_t)b * a.n_nodes + child] = 1;  // t == 0 -> identity (AR:146-148)
             } else if (!(eta <= F_THETA)) {
-                a.mode[(size_t)b * a.n_nodes + child] = 2;  // materialised by the Pade kernel
+                a.mode[(size_t)b * a.n_nodes + child] = 2;  // scaling-and-squaring path
             } else {
                 nc = taylor_ncoef(eta);
                 tau = t;
@@ -226,77 +322,112 @@ __global__ void __launch_bounds__(32 * F_MAXW) taylor_apply_kernel(ApplyArgs a) 
             p *= tau;
         }
     }
-    if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     __syncthreads();
 
-    // child vectors (one-hot / uniform / conditional-likelihood vector of an internal child)
-    const double unif = 1.0 / (double)n;  // AR:211
-    for (int x = warp; x < EB; x += nwarps) {
-        const int child = s_child[x], code = s_code[x];
-        const double* src =
-            (child >= 0 && code == -2) ? a.node_vec + ((size_t)b * a.n_nodes + child) * a.ldp : nullptr;
-        for (int j = lane; j < ldl; j += 32) {
-            double v = 0.0;
-            if (child >= 0 && j < n) v = (code >= 0) ? (j == code ? 1.0 : 0.0) : (code == -1 ? unif : src[j]);
-            Ls[(size_t)x * ldl + j] = v;
-        }
-    }
-    // chunks needed by this warp / by the CTA
+    // chunks needed by this warp / by the CTA, and which consumer warps have any work
     int wk = 0, ck = 0;
+    unsigned active = 0;
     for (int x = lane; x < EB; x += 32) {
         const int kc = (s_nc[x] + 3) >> 2;
         ck = max(ck, kc);
-        if (x >= warp * G * 8 && x < (warp + 1) * G * 8) wk = max(wk, kc);
+        if (kc > 0) active |= 1u << (x / (8 * G));
+        if (x / (8 * G) == warp) wk = max(wk, kc);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         wk = max(wk, __shfl_xor_sync(0xffffffffu, wk, o));
         ck = max(ck, __shfl_xor_sync(0xffffffffu, ck, o));
+        active |= __shfl_xor_sync(0xffffffffu, active, o);
     }
-    __syncthreads();
     if (ck == 0) return;  // nothing on the fused path in this CTA (uniform across the CTA)
 
     const int nj = npad >> 3;
     const int npass = (nj + F_JT - 1) / F_JT;
     const int nitems = (i_end - i_begin) * npass;
-    const double* tcb = a.tc + (size_t)b * n * F_KC * npad * 4;
+    const int stage_doubles = ck * F_JT * 32;
+    int ns = a.stage_doubles_cap / stage_doubles;
+    if (ns > F_MAXSTAGE) ns = F_MAXSTAGE;
 
-    auto issue = [&](int q) {
-        const int i = i_begin + q / npass, pass = q % npass;
-        const int j0 = pass * F_JT * 8;
-        const int ncols = min(F_JT * 8, npad - j0);
-        const uint32_t bytes = (uint32_t)ncols * 4 * sizeof(double);
-        uint64_t* bar = &full[q & 1];
-        mbar_expect_tx(bar, bytes * (uint32_t)ck);
-        double* dst = Bs + (size_t)(q & 1) * F_KC * F_JT * 32;
-        const double* src = tcb + ((size_t)i * F_KC * npad + j0) * 4;
-        for (int c = 0; c < ck; ++c)
-            bulk_g2s(dst + (size_t)c * F_JT * 32, src + (size_t)c * npad * 4, bytes, bar);
-    };
-    if (tid == 0 && nitems > 0) issue(0);
+    if (tid == 0) {
+        for (int s = 0; s < ns; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], __popc(active));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // child vectors (one-hot / uniform / conditional-likelihood vector of an internal child)
+    if (!LEAF) {
+        const double unif = 1.0 / (double)n;  // AR:211
+        for (int x = warp; x < EB; x += NW + 1) {
+            const int child = s_child[x], code = s_code[x];
+            const double* src = (child >= 0 && code == -2)
+                                    ? a.node_vec + ((size_t)b * a.n_nodes + child) * a.ldp : nullptr;
+            for (int j = lane; j < ldl; j += 32) {
+                double v = 0.0;
+                if (child >= 0 && j < n)
+                    v = (code >= 0) ? (j == code ? 1.0 : 0.0) : (code == -1 ? unif : src[j]);
+                Ls[(size_t)x * ldl + j] = v;
+            }
+        }
+    }
+    __syncthreads();
 
+    if (warp == NW) {
+        // ---- producer: one lane streams the (row, pass) tiles of the coefficient table
+        if (lane != 0) return;
+        const double* tcb = a.tc + (size_t)b * n * F_KC * npad * 4;
+        int s = 0, use = 0;
+        for (int i = i_begin; i < i_end; ++i) {
+            for (int pass = 0; pass < npass; ++pass) {
+                if (use > 0) {
+                    const uint32_t par = (uint32_t)((use - 1) & 1);
+                    while (!mbar_try_wait(&empty[s], par)) __nanosleep(64);
+                }
+                const int j0 = pass * F_JT * 8;
+                const int ncols = min(F_JT * 8, npad - j0);
+                const uint32_t bytes = (uint32_t)ncols * 4 * sizeof(double);
+                mbar_expect_tx(&full[s], bytes * (uint32_t)ck);
+                double* dst = Bs + (size_t)s * stage_doubles;
+                const double* src = tcb + ((size_t)i * F_KC * npad + j0) * 4;
+                for (int c = 0; c < ck; ++c)
+                    bulk_g2s(dst + (size_t)c * F_JT * 32, src + (size_t)c * npad * 4, bytes, &full[s]);
+                if (++s == ns) {
+                    s = 0;
+                    ++use;
+                }
+            }
+        }
+        return;
+    }
+    if (wk == 0) return;  // consumer warp without fused branches (not counted in `empty`)
+
+    // ---- consumers
     const long long floor_bits = __double_as_longlong(1e-12);
-    double rs[G], dt[G];
-    int bad[G];
+    // LEAF: the lane / tile / half that holds column `code` of each of the warp's groups
+    int my_jt[G], my_half[G];
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
-        rs[gi] = 0.0;
-        dt[gi] = 0.0;
-        bad[gi] = 0;
-    }
-
-    for (int q = 0; q < nitems; ++q) {
-        if (tid == 0 && q + 1 < nitems) issue(q + 1);
-        const int i = i_begin + q / npass, pass = q % npass;
-        const int j0 = pass * F_JT * 8;
-        const int njt = min(F_JT, nj - pass * F_JT);
-        if (wk > 0) {
-            while (!mbar_try_wait(&full[q & 1], (uint32_t)((q >> 1) & 1))) {
+        my_jt[gi] = -1;
+        my_half[gi] = 0;
+        if (MODE == APPLY_LEAF) {
+            const int code = s_code[(warp * G + gi) * 8 + g];
+            if (code >= 0 && ((code >> 1) & 3) == t4) {
+                my_jt[gi] = code >> 3;   // tile index along the whole row (pass * F_JT + jt)
+                my_half[gi] = code & 1;
             }
+        }
+    }
+    double rs0[G], rs1[G], dt0[G], dt1[G];
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) rs0[gi] = rs1[gi] = dt0[gi] = dt1[gi] = 0.0;
+    const double* Aw = As + (size_t)(warp * G) * F_KC * 32 + lane;
+    const bool has_pad = npad != n;
+    int s = 0;
+    uint32_t par = 0;
+    for (int i = i_begin; i < i_end; ++i) {
+        for (int pass = 0; pass < npass; ++pass) {
+            const int j0 = pass * F_JT * 8;
+            const int njt = min(F_JT, nj - pass * F_JT);
             double acc[G][F_JT][2];
 #pragma unroll
             for (int gi = 0; gi < G; ++gi)
@@ -305,70 +436,93 @@ __global__ void __launch_bounds__(32 * F_MAXW) taylor_apply_kernel(ApplyArgs a) 
                     acc[gi][jt][0] = 0.0;
                     acc[gi][jt][1] = 0.0;
                 }
-            const double* Bq = Bs + (size_t)(q & 1) * F_KC * F_JT * 32 + lane;
-            const double* Aw = As + (size_t)(warp * G) * F_KC * 32 + lane;
+            mbar_wait(&full[s], par);
+            const double* Bq = Bs + (size_t)s * stage_doubles + lane;
             for (int c = 0; c < wk; ++c) {
                 double av[G];
 #pragma unroll
                 for (int gi = 0; gi < G; ++gi) av[gi] = Aw[(size_t)(gi * F_KC + c) * 32];
                 const double* Bc = Bq + (size_t)c * F_JT * 32;
+                // tiles beyond njt (last pass of a wide row) multiply stale shared memory; their
+                // accumulators are never read
 #pragma unroll
                 for (int jt = 0; jt < F_JT; ++jt) {
-                    if (jt < njt) {
-                        const double bv = Bc[jt * 32];
+                    const double bv = Bc[jt * 32];
 #pragma unroll
-                        for (int gi = 0; gi < G; ++gi) dmma884(acc[gi][jt][0], acc[gi][jt][1], av[gi], bv);
+                    for (int gi = 0; gi < G; ++gi)
+                        dmma884(acc[gi][jt][0], acc[gi][jt][1], av[gi], bv);
+                }
+            }
+            // every shared-memory read of this stage has been consumed by an issued DMMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == ns) {
+                s = 0;
+                par ^= 1u;
+            }
+
+            if (EVAL) {
+#pragma unroll
+                for (int gi = 0; gi < G; ++gi) {
+                    const int x = (warp * G + gi) * 8 + g;
+                    if (s_nc[x] > 0) {
+                        double* xrow = a.X + ((size_t)s_child[x] * n + i) * a.ldp + j0 + 2 * t4;
+#pragma unroll
+                        for (int jt = 0; jt < F_JT; ++jt) {
+                            if (jt < njt && j0 + jt * 8 + 2 * t4 < a.ldp)
+                                *reinterpret_cast<double2*>(xrow + jt * 8) =
+                                    make_double2(acc[gi][jt][0], acc[gi][jt][1]);
+                        }
                     }
                 }
+                continue;
             }
             // floor, row sum and dot product with L_child on the accumulator fragments
 #pragma unroll
             for (int gi = 0; gi < G; ++gi) {
                 const double* Lrow = Ls + (size_t)((warp * G + gi) * 8 + g) * ldl + j0 + 2 * t4;
+                const int sel_jt = my_jt[gi] - pass * F_JT;
 #pragma unroll
                 for (int jt = 0; jt < F_JT; ++jt) {
-                    if (jt < njt) {
-                        const int j = j0 + jt * 8 + 2 * t4;
+                    if (njt == F_JT || jt < njt) {
                         double p0 = acc[gi][jt][0], p1 = acc[gi][jt][1];
-                        const long long b0 = __double_as_longlong(p0), b1 = __double_as_longlong(p1);
-                        if (b0 < floor_bits) p0 = 1e-12;  // np.maximum(P, 1e-12), AR:153
-                        if (b1 < floor_bits) p1 = 1e-12;
-                        if (j >= n) p0 = 0.0;             // padding columns
-                        if (j + 1 >= n) p1 = 0.0;
-                        const int h0 = __double2hiint(p0), h1 = __double2hiint(p1);
-                        bad[gi] |= ((h0 & 0x7ff00000) == 0x7ff00000) | ((h1 & 0x7ff00000) == 0x7ff00000);
-                        const double2 l = *reinterpret_cast<const double2*>(Lrow + jt * 8);
-                        rs[gi] += p0;
-                        rs[gi] += p1;
-                        dt[gi] = fma(p0, l.x, dt[gi]);
-                        dt[gi] = fma(p1, l.y, dt[gi]);
+                        if (__double_as_longlong(p0) < floor_bits) p0 = 1e-12;  // AR:153
+                        if (__double_as_longlong(p1) < floor_bits) p1 = 1e-12;
+                        if (has_pad && jt == njt - 1) {  // the tile holding the padding columns
+                            const int j = j0 + jt * 8 + 2 * t4;
+                            if (j >= n) p0 = 0.0;
+                            if (j + 1 >= n) p1 = 0.0;
+                        }
+                        rs0[gi] += p0;
+                        rs1[gi] += p1;
+                        if (MODE == APPLY_LEAF) {
+                            if (jt == sel_jt) dt0[gi] = my_half[gi] ? p1 : p0;
+                        } else {
+                            const double2 l = *reinterpret_cast<const double2*>(Lrow + jt * 8);
+                            dt0[gi] = fma(p0, l.x, dt0[gi]);
+                            dt1[gi] = fma(p1, l.y, dt1[gi]);
+                        }
                     }
                 }
             }
             if (pass == npass - 1) {
 #pragma unroll
                 for (int gi = 0; gi < G; ++gi) {
-                    double r = rs[gi], d = dt[gi];
-                    int bd = bad[gi];
+                    double r = rs0[gi] + rs1[gi], d = dt0[gi] + dt1[gi];
                     r += __shfl_xor_sync(0xffffffffu, r, 1);
                     d += __shfl_xor_sync(0xffffffffu, d, 1);
-                    bd |= __shfl_xor_sync(0xffffffffu, bd, 1);
                     r += __shfl_xor_sync(0xffffffffu, r, 2);
                     d += __shfl_xor_sync(0xffffffffu, d, 2);
-                    bd |= __shfl_xor_sync(0xffffffffu, bd, 2);
                     const int x = (warp * G + gi) * 8 + g;
                     if (t4 == 0 && s_nc[x] > 0) {
-                        const int child = s_child[x];
-                        a.w[((size_t)b * a.n_nodes + child) * a.ldp + i] = d / r;   // AR:154, AR:237
-                        if (bd) a.mode[(size_t)b * a.n_nodes + child] = 1;          // NaN -> I, AR:156-159
+                        const size_t o = ((size_t)b * a.n_nodes + s_child[x]) * a.ldp + i;
+                        a.w[o] = d;    // the combine kernel forms d / r (AR:154, AR:237)
+                        a.wr[o] = r;
                     }
-                    rs[gi] = 0.0;
-                    dt[gi] = 0.0;
-                    bad[gi] = 0;
+                    rs0[gi] = rs1[gi] = dt0[gi] = dt1[gi] = 0.0;
                 }
             }
         }
-        __syncthreads();
     }
 }
 
@@ -388,7 +542,8 @@ __device__ double block_sum_ct(double v, double* red) {
 // the per-branch vectors w = P @ L_child (fused path), L_child itself (P = I) or a streamed
 // materialised P (Pade path), with the reference's conditional rescale after every child.
 __global__ void __launch_bounds__(CT) combine_level_kernel(
-    const double* __restrict__ w, const uint8_t* __restrict__ mode, const double* __restrict__ P,
+    const double* __restrict__ w, const double* __restrict__ wr, const uint8_t* __restrict__ mode,
+    const double* __restrict__ P,
     const int32_t* __restrict__ slot, int E, int n, int ldp, int n_nodes, int root,
     const int32_t* __restrict__ level_nodes, const int32_t* __restrict__ child_off,
     const int32_t* __restrict__ child_idx, const int32_t* __restrict__ branch_of,
@@ -408,11 +563,33 @@ __global__ void __launch_bounds__(CT) combine_level_kernel(
     for (int ci = c_begin; ci < c_end; ++ci) {
         const int child = child_idx[ci];
         const int code = leaf_code[child];
-        const int md = mode[(size_t)b * n_nodes + child];
+        int md = mode[(size_t)b * n_nodes + child];
         const double* cv = node_vec + ((size_t)b * n_nodes + child) * ldp;
+        double fac[(CEVB_MAX_N + CT - 1) / CT];
         if (md == 0) {
+            // a NaN or +inf entry of P makes its row sum non-finite: the reference then finds
+            // NaN in P / rowsum and returns the identity for the whole matrix (AR:156-159)
             const double* wv = w + ((size_t)b * n_nodes + child) * ldp;
-            for (int i = tid; i < n; i += CT) v[i] *= wv[i];
+            const double* rv = wr + ((size_t)b * n_nodes + child) * ldp;
+            int bad = 0;
+#pragma unroll
+            for (int k = 0; k < (CEVB_MAX_N + CT - 1) / CT; ++k) {
+                const int i = tid + k * CT;
+                fac[k] = 1.0;
+                if (i < n) {
+                    const double r = rv[i];
+                    bad |= !(fabs(r) < INFINITY);
+                    fac[k] = wv[i] / r;
+                }
+            }
+            if (__syncthreads_or(bad)) md = 1;
+        }
+        if (md == 0) {
+#pragma unroll
+            for (int k = 0; k < (CEVB_MAX_N + CT - 1) / CT; ++k) {
+                const int i = tid + k * CT;
+                if (i < n) v[i] *= fac[k];
+            }
         } else if (md == 1) {
             for (int i = tid; i < n; i += CT)
                 v[i] *= (code >= 0) ? (i == code ? 1.0 : 0.0) : (code == -1 ? unif : cv[i]);
@@ -494,51 +671,177 @@ static int fused_query() {
     return 0;
 }
 
-static int launch_apply(const double* tc, const double* norms, int B, int n, int n_nodes,
-                        const int32_t* items, int n_items, const double* t_node,
-                        const int32_t* leaf_code, const double* node_vec, double* w, uint8_t* mode,
-                        cudaStream_t st) {
-    if (n_items <= 0 || B <= 0) return 0;
-    if (fused_query() != 0) return -2;
-    ApplyArgs a;
-    a.tc = tc; a.norms = norms; a.items = items; a.t_node = t_node; a.leaf_code = leaf_code;
-    a.node_vec = node_vec; a.w = w; a.mode = mode;
-    a.n_items = n_items; a.n = n; a.npad = round_up(n, 8); a.ldp = ldp_of(n); a.n_nodes = n_nodes;
-    a.ldl = a.npad + ((a.npad % 16) == 0 ? 8 : 0);
-    // groups per warp: 2 while the child vectors of 128 branches fit beside the staging buffers
-    int G = (apply_smem_bytes(F_MAXW, 2, a.ldl) <= g_f_optin) ? 2 : 1;
-    int nw = F_MAXW;
-    while (nw > 1 && apply_smem_bytes(nw, G, a.ldl) > g_f_optin) nw >>= 1;
-    if (apply_smem_bytes(nw, G, a.ldl) > g_f_optin) {
-        set_error("taylor_apply: n=%d does not fit in shared memory", n);
-        return -1;
-    }
-    const int need = (n_items + 8 * G - 1) / (8 * G);
-    if (need < nw) nw = need;
-    const int EB = nw * G * 8;
-    const int gx = (n_items + EB - 1) / EB;
+template <int G, int NW, int MODE>
+static int launch_apply_variant(ApplyArgs& a, int B, cudaStream_t st) {
+    constexpr int EB = NW * G * 8;
+    const size_t fixed = apply_fixed_bytes(EB, MODE != APPLY_GENERAL ? 0 : a.ldl);
+    const size_t one_stage = sizeof(double) * (size_t)F_KC * F_JT * 32;
+    if (fixed + one_stage > g_f_optin) return 1;  // does not fit: caller tries a smaller variant
+    size_t ring = g_f_optin - fixed;
+    const size_t ring_max = (NW >= 16 ? F_MAXSTAGE : 2) * one_stage;  // narrow CTAs: leave room for 2-3 per SM
+    if (ring > ring_max) ring = ring_max;
+    a.stage_doubles_cap = (int)(ring / sizeof(double));
+    const size_t smem = fixed + ring;
+    const int gx = (a.n_items + EB - 1) / EB;
     const long long want = 4LL * g_f_sm;
     int ry = 1;
     if ((long long)gx * B < want) {
         ry = (int)((want + (long long)gx * B - 1) / ((long long)gx * B));
-        const int ry_max = (n + 7) / 8;
+        const int ry_max = (a.n + 7) / 8;
         if (ry > ry_max) ry = ry_max;
     }
-    a.rows_per_cta = (n + ry - 1) / ry;
-    ry = (n + a.rows_per_cta - 1) / a.rows_per_cta;
-    const size_t smem = apply_smem_bytes(nw, G, a.ldl);
+    a.rows_per_cta = (a.n + ry - 1) / ry;
+    ry = (a.n + a.rows_per_cta - 1) / a.rows_per_cta;
     dim3 grid(gx, ry, B);
-    if (G == 2) {
-        CEVB_CHECK_CUDA(cudaFuncSetAttribute(taylor_apply_kernel<2>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        taylor_apply_kernel<2><<<grid, 32 * nw, smem, st>>>(a);
-    } else {
-        CEVB_CHECK_CUDA(cudaFuncSetAttribute(taylor_apply_kernel<1>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        taylor_apply_kernel<1><<<grid, 32 * nw, smem, st>>>(a);
-    }
+    CEVB_CHECK_CUDA(cudaFuncSetAttribute(taylor_apply_kernel<G, NW, MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    taylor_apply_kernel<G, NW, MODE><<<grid, 32 * (NW + 1), smem, st>>>(a);
     CEVB_CHECK_LAUNCH("taylor_apply_kernel");
     return 0;
+}
+
+template <int MODE>
+static int launch_apply_shapes(ApplyArgs& a, int B, cudaStream_t st) {
+    // CTA shapes from widest to narrowest; small launches use fewer warps so that more CTAs fit
+    int rc = 1;
+    if (a.n_items > 64) rc = launch_apply_variant<1, 16, MODE>(a, B, st);
+    if (rc == 1 && a.n_items > 32) rc = launch_apply_variant<1, 8, MODE>(a, B, st);
+    if (rc == 1 && a.n_items > 16) rc = launch_apply_variant<1, 4, MODE>(a, B, st);
+    if (rc == 1) rc = launch_apply_variant<1, 2, MODE>(a, B, st);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Squaring + post-processing of the pairs with t ||Q||_1 > theta: X <- X^(2^s) on the FP64
+// tensor cores with both matrices resident in shared memory, then max(X, 1e-12), row
+// renormalisation, NaN -> identity (AR:153-159), written back over X.  Persistent CTAs pull
+// work-list positions from an atomic counter.
+constexpr int SQ_NT = 512;
+constexpr int SQ_NW = SQ_NT / 32;
+
+__host__ __device__ inline size_t square_smem_bytes(int npad) {
+    return sizeof(double) * 2 * (size_t)npad * (npad + 4) + 64;
+}
+
+__global__ void __launch_bounds__(SQ_NT, 1) square_post_kernel(double* __restrict__ X,
+                                                               const int32_t* __restrict__ work_s,
+                                                               const unsigned int* __restrict__ count,
+                                                               long long cap, unsigned int* counter,
+                                                               int n, int ldp, int npad,
+                                                               int32_t* __restrict__ nan_count) {
+    extern __shared__ __align__(16) double smq[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int ldw = npad + 4, n8 = npad >> 3;
+    double* buf0 = smq;
+    double* buf1 = smq + (size_t)npad * ldw;
+    int* sh_q = reinterpret_cast<int*>(buf1 + (size_t)npad * ldw);
+    long long lim = (long long)*count;
+    if (lim > cap) lim = cap;
+    // column tiles are split into nch nearly equal chunks of at most 4 tiles
+    const int nch = (n8 + 3) >> 2, cbase = n8 / nch, cextra = n8 % nch;
+    for (;;) {
+        if (tid == 0) sh_q[0] = (int)atomicAdd(counter, 1u);
+        __syncthreads();
+        const long long q = (long long)(unsigned)sh_q[0];
+        if (q >= lim) break;
+        double* Xm = X + (size_t)q * n * ldp;
+        const int s = work_s[q];
+        // load (zero padding rows / columns)
+        for (int i = warp; i < npad; i += SQ_NW) {
+            for (int j = 2 * lane; j < ldw; j += 64) {
+                double2 v = make_double2(0.0, 0.0);
+                if (i < n && j < ldp) {
+                    v = *reinterpret_cast<const double2*>(Xm + (size_t)i * ldp + j);
+                    if (j + 1 >= n) v.y = 0.0;
+                }
+                *reinterpret_cast<double2*>(buf0 + (size_t)i * ldw + j) = v;
+            }
+        }
+        __syncthreads();
+        double* src = buf0;
+        double* dst = buf1;
+        for (int it = 0; it < s; ++it) {
+            const int ntask = n8 * nch;
+            for (int task = warp; task < ntask; task += SQ_NW) {
+                const int ch = task / n8, rt = task - ch * n8;
+                const int ct0 = ch * cbase + min(ch, cextra);
+                const int nct = cbase + (ch < cextra ? 1 : 0);
+                double acc[4][2] = {};
+                const double* arow = src + (size_t)(rt * 8 + g) * ldw + t4;
+                const double* bcol = src + (size_t)t4 * ldw + ct0 * 8 + g;
+                for (int k4 = 0; k4 < npad; k4 += 4) {
+                    const double av = arow[k4];
+                    const double* bp = bcol + (size_t)k4 * ldw;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < nct) dmma884(acc[c][0], acc[c][1], av, bp[c * 8]);
+                }
+                double* drow = dst + (size_t)(rt * 8 + g) * ldw + ct0 * 8 + 2 * t4;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < nct)
+                        *reinterpret_cast<double2*>(drow + c * 8) = make_double2(acc[c][0], acc[c][1]);
+            }
+            __syncthreads();
+            double* tmp = src;
+            src = dst;
+            dst = tmp;
+        }
+        // floor, renormalise, NaN check, store (AR:153-159)
+        int nanflag = 0;
+        for (int i = warp; i < n; i += SQ_NW) {
+            const double* xr = src + (size_t)i * ldw;
+            double rs = 0.0;
+            for (int j = 2 * lane; j < ldp; j += 64) {
+                const double2 x = *reinterpret_cast<const double2*>(xr + j);
+                const double a0 = (x.x != x.x) ? x.x : fmax(x.x, 1e-12);
+                const double a1 = (j + 1 < n) ? ((x.y != x.y) ? x.y : fmax(x.y, 1e-12)) : 0.0;
+                rs += a0 + a1;
+            }
+            rs = warp_sum(rs);
+            for (int j = 2 * lane; j < ldp; j += 64) {
+                const double2 x = *reinterpret_cast<const double2*>(xr + j);
+                double2 o;
+                o.x = ((x.x != x.x) ? x.x : fmax(x.x, 1e-12)) / rs;
+                o.y = (j + 1 < n) ? ((x.y != x.y) ? x.y : fmax(x.y, 1e-12)) / rs : 0.0;
+                if (o.x != o.x || o.y != o.y) nanflag = 1;
+                *reinterpret_cast<double2*>(Xm + (size_t)i * ldp + j) = o;
+            }
+        }
+        nanflag = __syncthreads_or(nanflag);
+        if (nanflag) {
+            for (int i = warp; i < n; i += SQ_NW)
+                for (int j = lane; j < ldp; j += 32) Xm[(size_t)i * ldp + j] = (i == j) ? 1.0 : 0.0;
+            if (tid == 0 && nan_count != nullptr) atomicAdd(nan_count, 1);
+        }
+        __syncthreads();
+    }
+}
+
+static int launch_apply(const double* tc, const double* norms, int B, int n, int n_nodes,
+                        const int32_t* items, int n_items, int leaf_only, const double* t_node,
+                        const int32_t* leaf_code, const double* node_vec, double* w, double* wr,
+                        uint8_t* mode, cudaStream_t st) {
+    if (n_items <= 0 || B <= 0) return 0;
+    if (fused_query() != 0) return -2;
+    if (n > CEVB_MAX_N) {
+        set_error("taylor_apply: n=%d exceeds CEVB_MAX_N=%d", n, CEVB_MAX_N);
+        return -1;
+    }
+    ApplyArgs a;
+    a.tc = tc; a.norms = norms; a.items = items; a.t_node = t_node; a.leaf_code = leaf_code;
+    a.node_vec = node_vec; a.w = w; a.wr = wr; a.mode = mode;
+    a.n_items = n_items; a.n = n; a.npad = round_up(n, 8); a.ldp = ldp_of(n); a.n_nodes = n_nodes;
+    a.ldl = a.npad + ((a.npad % 16) == 0 ? 8 : 0);
+    a.slot = nullptr; a.X = nullptr; a.E = 0;
+    const int rc = leaf_only ? launch_apply_shapes<APPLY_LEAF>(a, B, st)
+                             : launch_apply_shapes<APPLY_GENERAL>(a, B, st);
+    if (rc == 1) {
+        set_error("taylor_apply: n=%d does not fit in shared memory", n);
+        return -1;
+    }
+    return rc;
 }
 
 }  // namespace cevb
@@ -549,43 +852,97 @@ extern "C" size_t cevb_taylor_doubles(int n) {
     return (size_t)n * F_KC * round_up(n, 8) * 4;
 }
 
-extern "C" int cevb_taylor_prepare(const double* pw, const uint16_t* csc, const uint8_t* csc_cnt,
-                                   int B, int n, double* tc, void* stream) {
+extern "C" int cevb_taylor_prepare(const double* pw, int B, int n, double* norms, uint16_t* csc,
+                                   uint8_t* csc_cnt, double* tc, void* stream) {
     if (B <= 0) return 0;
     if (B > 65535) {
         set_error("cevb_taylor_prepare: B=%d exceeds one launch; chunk the batch", B);
         return -1;
     }
+    cudaStream_t st = (cudaStream_t)stream;
     const int npad = round_up(n, 8);
+    q_structure_kernel<<<B, 128, 0, st>>>(pw, n, ldq_of(n), norms, csc, csc_cnt);
+    CEVB_CHECK_LAUNCH("q_structure_kernel");
     dim3 grid(n, B);
-    taylor_coeff_kernel<<<grid, 128, sizeof(double) * 6 * (size_t)npad, (cudaStream_t)stream>>>(
-        pw, csc, csc_cnt, n, ldq_of(n), npad, tc);
+    taylor_coeff_kernel<<<grid, 128, sizeof(double) * 6 * (size_t)npad, st>>>(pw, csc, csc_cnt, n,
+                                                                             ldq_of(n), npad, tc);
     CEVB_CHECK_LAUNCH("taylor_coeff_kernel");
     return 0;
 }
 
 extern "C" int cevb_expm_plan(const double* norms, const double* t, int B, int E, long long cap,
-                              int32_t* slot, int32_t* worklist, unsigned int* count, void* stream) {
+                              int32_t* slot, int32_t* worklist, int32_t* work_s, unsigned int* count,
+                              void* stream) {
     if (B <= 0 || E <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     CEVB_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned int), st));
     const long long M = (long long)B * E;
     expm_plan_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(norms, t, E, M, cap, slot, worklist,
-                                                                count);
+                                                                work_s, count);
     CEVB_CHECK_LAUNCH("expm_plan_kernel");
     return 0;
 }
 
+extern "C" int cevb_taylor_matrices_supported(int n) {
+    if (fused_query() != 0) return 0;
+    return (n >= 2 && n <= CEVB_MAX_N && square_smem_bytes(round_up(n, 8)) <= g_f_optin) ? 1 : 0;
+}
+
+extern "C" int cevb_taylor_matrices(const double* tc, const double* norms, const double* t,
+                                    const int32_t* t_order, int B, int E, int n,
+                                    const int32_t* slot, const int32_t* work_s,
+                                    const unsigned int* count, long long cap, double* P,
+                                    unsigned int* counter, int32_t* nan_count, void* stream) {
+    if (B <= 0 || E <= 0 || cap <= 0) return 0;
+    if (B > 65535) {
+        set_error("cevb_taylor_matrices: B=%d exceeds one launch; chunk the batch", B);
+        return -1;
+    }
+    if (fused_query() != 0) return -2;
+    if (n > CEVB_MAX_N) {
+        set_error("cevb_taylor_matrices: n=%d exceeds CEVB_MAX_N=%d", n, CEVB_MAX_N);
+        return -1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    ApplyArgs a;
+    a.tc = tc; a.norms = norms; a.items = t_order; a.t_node = t; a.leaf_code = nullptr;
+    a.node_vec = nullptr; a.w = nullptr; a.wr = nullptr; a.mode = nullptr;
+    a.n_items = E; a.n = n; a.npad = round_up(n, 8); a.ldp = ldp_of(n); a.n_nodes = 0;
+    a.ldl = 0;
+    a.slot = slot; a.X = P; a.E = E;
+    int rc = launch_apply_shapes<APPLY_EVAL>(a, B, st);
+    if (rc == 1) {
+        set_error("cevb_taylor_matrices: n=%d does not fit in shared memory", n);
+        return -1;
+    }
+    if (rc != 0) return rc;
+    const size_t smem = square_smem_bytes(a.npad);
+    if (smem > g_f_optin) {
+        set_error("cevb_taylor_matrices: squaring n=%d needs %zu B of shared memory", n, smem);
+        return -1;
+    }
+    CEVB_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    CEVB_CHECK_CUDA(cudaFuncSetAttribute(square_post_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = g_f_sm;
+    if (grid > cap) grid = cap;
+    square_post_kernel<<<(unsigned)grid, SQ_NT, smem, st>>>(P, work_s, count, cap, counter, n, a.ldp,
+                                                            a.npad, nan_count);
+    CEVB_CHECK_LAUNCH("square_post_kernel");
+    return 0;
+}
+
 extern "C" int cevb_taylor_apply(const double* tc, const double* norms, int B, int n, int n_nodes,
-                                 const int32_t* items, int n_items, const double* t_node,
-                                 const int32_t* leaf_code, const double* node_vec, double* w,
-                                 uint8_t* mode, void* stream) {
+                                 const int32_t* items, int n_items, int leaf_only,
+                                 const double* t_node, const int32_t* leaf_code,
+                                 const double* node_vec, double* w, double* wr, uint8_t* mode,
+                                 void* stream) {
     if (B > 65535) {
         set_error("cevb_taylor_apply: B=%d exceeds one launch; chunk the batch", B);
         return -1;
     }
-    return launch_apply(tc, norms, B, n, n_nodes, items, n_items, t_node, leaf_code, node_vec, w,
-                        mode, (cudaStream_t)stream);
+    return launch_apply(tc, norms, B, n, n_nodes, items, n_items, leaf_only, t_node, leaf_code,
+                        node_vec, w, wr, mode, (cudaStream_t)stream);
 }
 
 extern "C" int cevb_prune_fused(const double* tc, const double* norms, const double* P,
@@ -594,8 +951,9 @@ extern "C" int cevb_prune_fused(const double* tc, const double* norms, const dou
                                 int n_levels, const int32_t* child_off, const int32_t* child_idx,
                                 const int32_t* branch_of, const int32_t* leaf_code,
                                 const int32_t* level_child, const int32_t* level_child_off_host,
-                                const double* t_node, const double* root_freq, double* node_vec,
-                                double* w, uint8_t* mode, double* logl, int32_t* rescales,
+                                const int32_t* level_child_nleaf_host, const double* t_node,
+                                const double* root_freq, double* node_vec, double* w, double* wr,
+                                uint8_t* mode, double* logl, int32_t* rescales,
                                 int level_begin, int level_end, int stages, void* stream) {
     if (B <= 0) return 0;
     if (B > 65535) {
@@ -618,15 +976,20 @@ extern "C" int cevb_prune_fused(const double* tc, const double* norms, const dou
         const int cnt = level_off_host[lv + 1] - level_off_host[lv];
         if (cnt <= 0) continue;
         if (stages & CEVB_FUSED_APPLY) {
+            // observed-leaf children first (one-hot child vectors), then the others
             const int c0 = level_child_off_host[lv], c1 = level_child_off_host[lv + 1];
-            const int rc = launch_apply(tc, norms, B, n, n_nodes, level_child + c0, c1 - c0, t_node,
-                                        leaf_code, node_vec, w, mode, st);
+            const int nl = level_child_nleaf_host ? level_child_nleaf_host[lv] : 0;
+            int rc = launch_apply(tc, norms, B, n, n_nodes, level_child + c0, nl, 1, t_node, leaf_code,
+                                  node_vec, w, wr, mode, st);
+            if (rc != 0) return rc;
+            rc = launch_apply(tc, norms, B, n, n_nodes, level_child + c0 + nl, c1 - c0 - nl, 0, t_node,
+                              leaf_code, node_vec, w, wr, mode, st);
             if (rc != 0) return rc;
         }
         if (stages & CEVB_FUSED_COMBINE) {
             dim3 grid(cnt, B);
             combine_level_kernel<<<grid, CT, csmem, st>>>(
-                w, mode, P, slot, E, n, ldp, n_nodes, root, level_nodes + level_off_host[lv],
+                w, wr, mode, P, slot, E, n, ldp, n_nodes, root, level_nodes + level_off_host[lv],
                 child_off, child_idx, branch_of, leaf_code, root_freq, node_vec, logl, rescales);
             CEVB_CHECK_LAUNCH("combine_level_kernel");
         }

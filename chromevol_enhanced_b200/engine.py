@@ -74,8 +74,11 @@ class ExpmWorkspace:
             self.tc = torch.empty((cap, lib.cevb_taylor_doubles(n)), **f64)
             self.slot = torch.empty((cap, n_t), dtype=torch.int32, device=device)
             self.worklist = torch.empty(max(self.p_slots, 1), dtype=torch.int32, device=device)
+            self.work_s = torch.zeros(max(self.p_slots, 1), dtype=torch.int32, device=device)
+            self.nan_count = torch.zeros(1, dtype=torch.int32, device=device)
             self.work_count = torch.zeros(1, dtype=torch.int32, device=device)
             self.w = torch.zeros((cap, n_nodes, self.ldp), **f64)
+            self.wr = torch.ones((cap, n_nodes, self.ldp), **f64)
             self.mode = torch.zeros((cap, n_nodes), dtype=torch.uint8, device=device)
         scratch_bytes = lib.cevb_expm_scratch_bytes(n)
         grid = lib.cevb_expm_grid(n, cap * n_t)
@@ -92,11 +95,20 @@ class LikelihoodEngine:
     """Tree + data resident on the device; evaluates batches of parameter vectors."""
 
     def __init__(self, flat: FlatTree, device=None, max_workspace_bytes=32 << 30, chunk=None,
-                 path="fused"):
+                 path="fused", squaring="series"):
+        """path: "fused" (series on the tensor cores, P never written for t||Q||_1 <= 5.4) or
+        "materialised" (every P by the Pade kernel).  squaring: how the fused path forms the
+        matrices that need scaling and squaring -- "series" (series at t 2^-s + squarings in
+        shared memory) or "pade" (the scipy-algorithm kernel on a work list)."""
         _lib.require_device()
         if path not in ("fused", "materialised"):
             raise ValueError("path must be 'fused' or 'materialised'")
+        if squaring not in ("series", "pade"):
+            raise ValueError("squaring must be 'series' or 'pade'")
         self.path = path
+        if squaring == "series" and not _lib.load().cevb_taylor_matrices_supported(flat.n_states):
+            squaring = "pade"     # two n x n matrices do not fit in shared memory
+        self.squaring = squaring
         self.lib = _lib.load()
         self.flat = flat
         self.device = torch.device(device if device is not None else
@@ -113,14 +125,17 @@ class LikelihoodEngine:
         self.h_level_off = np.ascontiguousarray(flat.level_off, dtype=np.int32)
         self.d_level_child = torch.as_tensor(flat.level_child, **i32)
         self.h_level_child_off = np.ascontiguousarray(flat.level_child_off, dtype=np.int32)
+        self.h_level_child_nleaf = np.ascontiguousarray(flat.level_child_nleaf, dtype=np.int32)
         self.d_t_node = torch.as_tensor(flat.dist_eff, dtype=torch.float64, device=self.device)
+        self.d_t_order = torch.as_tensor(np.argsort(-np.nan_to_num(flat.t_unique), kind="stable")
+                                         .astype(np.int32), device=self.device)
         mat_bytes = 8 * self.n * self.ldp
         if path == "fused":
             # per vector: powers + series coefficients + node vectors + w; the rest of the budget
             # holds materialised matrices (only pairs with t ||Q||_1 > 5.4 need one)
             per_vec = (8 * 7 * self.n * self.lib.cevb_ldq(self.n)
                        + 8 * self.lib.cevb_taylor_doubles(self.n)
-                       + 16 * flat.n_nodes * self.ldp + 16 * flat.n_t + 64 * self.n)
+                       + 24 * flat.n_nodes * self.ldp + 16 * flat.n_t + 64 * self.n)
             if chunk is None:
                 chunk = max(1, min(4096, int((max_workspace_bytes // 2) // max(per_vec, 1))))
             self.p_budget = max(int(max_workspace_bytes) - int(chunk) * per_vec,
@@ -210,20 +225,30 @@ class LikelihoodEngine:
         e0 = self._mark("prepare")
         _lib.check(lib.cevb_build_q(_lib.ptr(ws.params), nb, self.n, _lib.ptr(ws.pw), st),
                    "cevb_build_q")
-        _lib.check(lib.cevb_expm_prepare(_lib.ptr(ws.pw), nb, self.n, _lib.ptr(ws.norms),
-                                         _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt), st),
-                   "cevb_expm_prepare")
-        _lib.check(lib.cevb_taylor_prepare(_lib.ptr(ws.pw), _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt),
-                                           nb, self.n, _lib.ptr(ws.tc), st), "cevb_taylor_prepare")
+        _lib.check(lib.cevb_taylor_prepare(_lib.ptr(ws.pw), nb, self.n, _lib.ptr(ws.norms),
+                                           _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt), _lib.ptr(ws.tc),
+                                           st), "cevb_taylor_prepare")
         _lib.check(lib.cevb_expm_plan(_lib.ptr(ws.norms), _lib.ptr(self.d_t), nb, f.n_t,
                                       ws.p_slots, _lib.ptr(ws.slot), _lib.ptr(ws.worklist),
-                                      _lib.ptr(ws.work_count), st), "cevb_expm_plan")
+                                      _lib.ptr(ws.work_s), _lib.ptr(ws.work_count), st),
+                   "cevb_expm_plan")
         e1 = self._mark("prepare", e0)
-        _lib.check(lib.cevb_expm_branches_list(
-            _lib.ptr(ws.pw), _lib.ptr(ws.norms), _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt),
-            _lib.ptr(self.d_t), nb, f.n_t, self.n, _lib.ptr(ws.P), _lib.ptr(ws.info),
-            _lib.ptr(ws.scratch), _lib.ptr(ws.counter), full_pivot, _lib.ptr(ws.worklist),
-            _lib.ptr(ws.work_count), ws.p_slots, st), "cevb_expm_branches_list")
+        if self.squaring == "series":
+            _lib.check(lib.cevb_taylor_matrices(
+                _lib.ptr(ws.tc), _lib.ptr(ws.norms), _lib.ptr(self.d_t), _lib.ptr(self.d_t_order),
+                nb, f.n_t, self.n, _lib.ptr(ws.slot), _lib.ptr(ws.work_s), _lib.ptr(ws.work_count),
+                ws.p_slots, _lib.ptr(ws.P), _lib.ptr(ws.counter), _lib.ptr(ws.nan_count), st),
+                "cevb_taylor_matrices")
+        else:
+            # Pade-13 + scaling and squaring (the scipy algorithm) for the listed pairs
+            _lib.check(lib.cevb_expm_prepare(_lib.ptr(ws.pw), nb, self.n, _lib.ptr(ws.norms),
+                                             _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt), st),
+                       "cevb_expm_prepare")
+            _lib.check(lib.cevb_expm_branches_list(
+                _lib.ptr(ws.pw), _lib.ptr(ws.norms), _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt),
+                _lib.ptr(self.d_t), nb, f.n_t, self.n, _lib.ptr(ws.P), _lib.ptr(ws.info),
+                _lib.ptr(ws.scratch), _lib.ptr(ws.counter), full_pivot, _lib.ptr(ws.worklist),
+                _lib.ptr(ws.work_count), ws.p_slots, st), "cevb_expm_branches_list")
         e2 = self._mark("expm", e1)
 
         def prune(lo, hi, stages):
@@ -234,8 +259,9 @@ class LikelihoodEngine:
                 _lib.ptr(self.d_child_off), _lib.ptr(self.d_child_idx), _lib.ptr(self.d_branch_of),
                 _lib.ptr(self.d_leaf_code), _lib.ptr(self.d_level_child),
                 self.h_level_child_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                self.h_level_child_nleaf.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
                 _lib.ptr(self.d_t_node), _lib.ptr(d_root_freq), _lib.ptr(self._node_vec),
-                _lib.ptr(ws.w), _lib.ptr(ws.mode), _lib.ptr(self._logl), _lib.ptr(self._rescales),
+                _lib.ptr(ws.w), _lib.ptr(ws.wr), _lib.ptr(ws.mode), _lib.ptr(self._logl), _lib.ptr(self._rescales),
                 lo, hi, stages, st), "cevb_prune_fused")
 
         if self.stage_events is None:
@@ -256,11 +282,13 @@ class LikelihoodEngine:
         ws.params[:nb].copy_(d_params_chunk)
         if self.path == "fused":
             self._fused_chunk(ws, nb, d_root_freq, full_pivot)
-            self._growth_flag |= ((ws.info[:nb] >> 16) & INFO_GROWTH).any()
+            if self.squaring == "pade":
+                self._growth_flag |= ((ws.info[:nb] >> 16) & INFO_GROWTH).any()
             self._overflow_flag |= (ws.work_count[0] > ws.p_slots)
             self._materialised += ws.work_count[0].to(torch.int64)
             if self.keep_info:
-                self.info_log.append((ws.info[:nb].cpu().numpy().copy(),
+                cnt = int(min(int(ws.work_count[0]), ws.p_slots))
+                self.info_log.append((ws.work_s[:cnt].cpu().numpy().copy(),
                                       ws.slot[:nb].cpu().numpy().copy(),
                                       ws.norms[:nb, 0].cpu().numpy().copy()))
             return
@@ -273,11 +301,17 @@ class LikelihoodEngine:
 
     def launches_per_chunk(self):
         """Kernel launches of ours per chunk.  materialised: build_q, 4 power GEMMs, norms, order,
-        expm, leaf init and one pruning kernel per non-empty level.  fused: build_q, 4 power
-        GEMMs, norms, series coefficients, plan, order, expm (work list), leaf init and two
-        kernels (apply, combine) per non-empty level."""
+        expm, leaf init and one pruning kernel per non-empty level.  fused: build_q, Q structure,
+        series coefficients, plan, series matrices + squaring (or, squaring="pade": 4 power
+        GEMMs, norms, order, expm on the work list), leaf init, one combine kernel per non-empty
+        level and one apply kernel per non-empty (level, leaf / non-leaf) part."""
         levels = int(np.count_nonzero(np.diff(self.flat.level_off)))
-        return (11 + 2 * levels) if self.path == "fused" else (9 + levels)
+        if self.path != "fused":
+            return 9 + levels
+        nl = self.flat.level_child_nleaf
+        tot = np.diff(self.flat.level_child_off)
+        applies = int(np.count_nonzero(nl)) + int(np.count_nonzero(tot - nl))
+        return (7 if self.squaring == "series" else 12) + levels + applies
 
     # ------------------------------------------------------------------ public
     def log_likelihood(self, params, root_freq=None, check_growth=True):

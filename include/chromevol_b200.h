@@ -44,6 +44,7 @@ extern "C" {
 #define CEVB_NNORM 16
 #define CEVB_MAX_SPARSE 12
 #define CEVB_NEVENT 8
+#define CEVB_MAX_N 288           /* largest supported matrix order (states 0..287) */
 #define CEVB_TAYLOR_KC 10       /* chunks of 4 series coefficients kept per vector: degrees 0..39 */
 #define CEVB_FUSED_INIT 1
 #define CEVB_FUSED_APPLY 2
@@ -107,39 +108,58 @@ int cevb_expm_branches_list(const double* pw, const double* norms, const uint16_
                             long long work_cap, void* stream);
 
 /* ---- (2c) fused path tables.  All branches of a parameter vector share Q (AR:230-233 with no
- * branch_params), so expm(Q t) = sum_k t^k C_k with C_k = Q^k / k! formed once per vector:
+ * branch_params), so expm(Q t) = sum_k t^k C_k with C_k = Q^k / k! formed once per vector.
+ * cevb_taylor_prepare needs only slot 0 of pw (Q) and writes
+ *   norms[b][CEVB_NORM_ONE] = ||Q_b||_1, the compressed-column structure csc / csc_cnt and
  *   tc [B][n][CEVB_TAYLOR_KC][n_pad][4]   (n_pad = n rounded up to 8; cevb_taylor_doubles(n)
  *   doubles per vector); chunk c of row i holds degrees 4c..4c+3 interleaved per column.
- * cevb_expm_plan routes every (vector, branch length) pair with t ||Q||_1 > CEVB_TAYLOR_THETA
- * to the scaling-and-squaring kernel: slot [B][E] = position in worklist (-1 = fused path,
- * -2 = list overflow), *count = pairs found (may exceed cap; the caller then re-plans). */
+ * cevb_expm_plan lists every (vector, branch length) pair with t ||Q||_1 > CEVB_TAYLOR_THETA,
+ * which needs scaling and squaring and therefore a materialised matrix: slot [B][E] = position
+ * in worklist (-1 = fused path, -2 = list overflow), work_s [cap] = squarings of that position
+ * (may be NULL), *count = pairs found (may exceed cap; the caller then re-plans).
+ * cevb_taylor_matrices fills the P slots of a plan: the series at t 2^-s for all listed pairs
+ * of a vector at once (tensor cores, t_order = branch-length indices sorted by decreasing t),
+ * then s squarings and the AR:153-159 post-processing per matrix in shared memory.
+ * counter: one uint32 scratch; nan_count (may be NULL) += matrices that fell back to I. */
 size_t cevb_taylor_doubles(int n);
-int cevb_taylor_prepare(const double* pw, const uint16_t* csc, const uint8_t* csc_cnt, int B, int n,
-                        double* tc, void* stream);
+/* 1 when cevb_taylor_matrices can keep two n x n matrices in shared memory (n <= 112 on B200);
+ * larger orders use cevb_expm_branches_list for the pairs that need squarings */
+int cevb_taylor_matrices_supported(int n);
+int cevb_taylor_prepare(const double* pw, int B, int n, double* norms, uint16_t* csc,
+                        uint8_t* csc_cnt, double* tc, void* stream);
 int cevb_expm_plan(const double* norms, const double* t, int B, int E, long long cap, int32_t* slot,
-                   int32_t* worklist, unsigned int* count, void* stream);
+                   int32_t* worklist, int32_t* work_s, unsigned int* count, void* stream);
+int cevb_taylor_matrices(const double* tc, const double* norms, const double* t,
+                         const int32_t* t_order, int B, int E, int n, const int32_t* slot,
+                         const int32_t* work_s, const unsigned int* count, long long cap, double* P,
+                         unsigned int* counter, int32_t* nan_count, void* stream);
 
 /* ---- (2d+3) fused transition-probability x child-vector product, AR:136-166 + AR:237 without
  * materialising P: for every listed branch (items[k] = child node id, branch length
  * t_node[child]) and vector b,
- *   w[b][child][i] = sum_j P'[i][j] L_child[j],  P' = post(expm(Q_b t))
- * evaluated on the FP64 tensor cores from tc.  L_child is the one-hot / uniform leaf vector
+ *   w[b][child][i] / wr[b][child][i] = sum_j P'[i][j] L_child[j],  P' = post(expm(Q_b t)),
+ * (w = the sum over the floored entries, wr = their row sum, AR:153-154; a non-finite wr[i]
+ * means the reference would have found NaN and used the identity, AR:156-159)
+ * evaluated on the FP64 tensor cores from tc.  leaf_only = 1 promises that every listed child
+ * is an observed leaf (leaf_code >= 0) and selects the variant that stages no child vectors.  L_child is the one-hot / uniform leaf vector
  * (leaf_code >= 0 / == -1) or node_vec[b][child] (leaf_code == -2).  mode [B][n_nodes] must be
  * zero on entry; the kernel sets 1 where P is the identity (t == 0, NaN fallback) and 2 where
  * the pair is on the materialised path -- w is not written for those. */
 int cevb_taylor_apply(const double* tc, const double* norms, int B, int n, int n_nodes,
-                      const int32_t* items, int n_items, const double* t_node,
-                      const int32_t* leaf_code, const double* node_vec, double* w, uint8_t* mode,
-                      void* stream);
+                      const int32_t* items, int n_items, int leaf_only, const double* t_node,
+                      const int32_t* leaf_code, const double* node_vec, double* w, double* wr,
+                      uint8_t* mode, void* stream);
 
 /* Whole tree with the fused path: same contract and tree arrays as cevb_prune, plus
  *   level_child [n_branches]  child nodes grouped by the level of their parent (any order
  *                             inside a level; longest branches first packs the work best),
  *   level_child_off [n_levels+1] HOST offsets into level_child,
+ *   level_child_nleaf [n_levels] HOST: the first level_child_nleaf[lv] children of level lv
+ *                             are observed leaves (may be NULL = unknown),
  *   t_node [n_nodes]          effective branch length above every node,
  *   P / slot                  materialised matrices and slot map from cevb_expm_plan +
  *                             cevb_expm_branches_list (E = row length of slot),
- *   w [B][n_nodes][ldp], mode [B][n_nodes]   scratch.
+ *   w, wr [B][n_nodes][ldp], mode [B][n_nodes]   scratch.
  * Levels [level_begin, level_end) are processed; `stages` is a mask of CEVB_FUSED_INIT (zero
  * mode / rescales, write the leaf vectors), CEVB_FUSED_APPLY and CEVB_FUSED_COMBINE.  The whole
  * tree in one call is (0, n_levels, CEVB_FUSED_ALL); the split form lets a caller time the two
@@ -149,7 +169,8 @@ int cevb_prune_fused(const double* tc, const double* norms, const double* P, con
                      const int32_t* level_off_host, int n_levels, const int32_t* child_off,
                      const int32_t* child_idx, const int32_t* branch_of, const int32_t* leaf_code,
                      const int32_t* level_child, const int32_t* level_child_off_host,
-                     const double* t_node, const double* root_freq, double* node_vec, double* w,
+                     const int32_t* level_child_nleaf_host, const double* t_node,
+                     const double* root_freq, double* node_vec, double* w, double* wr,
                      uint8_t* mode, double* logl, int32_t* rescales, int level_begin, int level_end,
                      int stages, void* stream);
 

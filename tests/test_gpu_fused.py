@@ -37,11 +37,9 @@ def _apply(rows, times, N, child_vectors=None, codes=None):
     ws.params.copy_(torch.as_tensor(rows, device=dev))
     st = _stream_ptr()
     _lib.check(lib.cevb_build_q(_lib.ptr(ws.params), B, n, _lib.ptr(ws.pw), st), "build_q")
-    _lib.check(lib.cevb_expm_prepare(_lib.ptr(ws.pw), B, n, _lib.ptr(ws.norms), _lib.ptr(ws.csc),
-                                     _lib.ptr(ws.csc_cnt), st), "prepare")
     tc = torch.empty((B, lib.cevb_taylor_doubles(n)), dtype=torch.float64, device=dev)
-    _lib.check(lib.cevb_taylor_prepare(_lib.ptr(ws.pw), _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt), B, n,
-                                       _lib.ptr(tc), st), "taylor_prepare")
+    _lib.check(lib.cevb_taylor_prepare(_lib.ptr(ws.pw), B, n, _lib.ptr(ws.norms), _lib.ptr(ws.csc),
+                                       _lib.ptr(ws.csc_cnt), _lib.ptr(tc), st), "taylor_prepare")
     ldp = ws.ldp
     t_node = torch.as_tensor(np.repeat(times, K), device=dev)
     leaf_code = torch.as_tensor(np.tile(codes, E), device=dev)
@@ -51,13 +49,16 @@ def _apply(rows, times, N, child_vectors=None, codes=None):
         node_vec[:, :, :n] = cv.repeat(E, 1)[None]
     items = torch.arange(n_nodes, dtype=torch.int32, device=dev)
     w = torch.full((B, n_nodes, ldp), float("nan"), dtype=torch.float64, device=dev)
+    wr = torch.ones((B, n_nodes, ldp), dtype=torch.float64, device=dev)
     mode = torch.zeros((B, n_nodes), dtype=torch.uint8, device=dev)
+    leaf_only = int(bool((codes >= 0).all()))      # exercises the one-hot variant where it applies
     _lib.check(lib.cevb_taylor_apply(_lib.ptr(tc), _lib.ptr(ws.norms), B, n, n_nodes, _lib.ptr(items),
-                                     n_nodes, _lib.ptr(t_node), _lib.ptr(leaf_code), _lib.ptr(node_vec),
-                                     _lib.ptr(w), _lib.ptr(mode), st), "taylor_apply")
+                                     n_nodes, leaf_only, _lib.ptr(t_node), _lib.ptr(leaf_code),
+                                     _lib.ptr(node_vec), _lib.ptr(w), _lib.ptr(wr), _lib.ptr(mode), st),
+               "taylor_apply")
     torch.cuda.synchronize()
-    return (w[:, :, :n].cpu().numpy().reshape(B, E, K, n), mode.cpu().numpy().reshape(B, E, K),
-            ws.norms[:, 0].cpu().numpy())
+    w = (w / wr)[:, :, :n].cpu().numpy().reshape(B, E, K, n)          # AR:154
+    return w, mode.cpu().numpy().reshape(B, E, K), ws.norms[:, 0].cpu().numpy()
 
 
 @pytest.mark.parametrize("N", [35, 100])
@@ -85,6 +86,23 @@ def test_fused_p_columns_match_oracle(N):
                 assert np.abs(P - ref).max() <= 1e-12, (b, t, eta)
                 n_fused += 1
     assert n_fused > 40
+
+
+def test_fused_general_variant_on_one_hot_children():
+    """The same columns through the variant that stages child vectors (leaf_only = 0)."""
+    from chromevol_enhanced_b200 import synthetic
+    rows = synthetic.random_param_rows(3, seed=4, linear='positive')
+    rows[:, :5] *= 0.3
+    times = np.array([0.002, 0.03, 0.09])
+    N = 100
+    eye = np.eye(N + 1)
+    w, mode, norm1 = _apply(rows, times, N, child_vectors=eye, codes=np.full(N + 1, -2))
+    for b in range(rows.shape[0]):
+        Q = O.build_q(synthetic.row_to_dict(rows[b]), N)
+        for e, t in enumerate(times):
+            if t * norm1[b] > 5.4:
+                continue
+            assert np.abs(w[b, e].T - O.transition_probabilities(Q, t)).max() <= 1e-12
 
 
 def test_fused_p_eta_sweep_up_to_theta():
@@ -165,6 +183,131 @@ def test_fused_odd_sizes(N):
                 continue
             ref = O.transition_probabilities(Q, t)
             assert np.abs(w[b, e].T - ref).max() <= 1e-12, (N, b, t)
+
+
+def _series_matrices(rows, times, N):
+    """post(expm(Q_b t_e)) for the pairs with t ||Q||_1 > 5.4 through cevb_expm_plan +
+    cevb_taylor_matrices; returns (P[slot], slot[b, e], squarings[slot], nan_count)."""
+    import torch
+    from chromevol_enhanced_b200 import _lib
+    from chromevol_enhanced_b200.engine import ExpmWorkspace, _stream_ptr
+    _lib.require_device()
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    n = N + 1
+    rows = np.atleast_2d(np.asarray(rows, dtype=np.float64))
+    times = np.asarray(times, dtype=np.float64)
+    B, E = rows.shape[0], times.shape[0]
+    ws = ExpmWorkspace(n, E, B, dev, p_slots=B * E, n_nodes=1)
+    ws.params.copy_(torch.as_tensor(rows, device=dev))
+    st = _stream_ptr()
+    _lib.check(lib.cevb_build_q(_lib.ptr(ws.params), B, n, _lib.ptr(ws.pw), st), "build_q")
+    _lib.check(lib.cevb_taylor_prepare(_lib.ptr(ws.pw), B, n, _lib.ptr(ws.norms), _lib.ptr(ws.csc),
+                                       _lib.ptr(ws.csc_cnt), _lib.ptr(ws.tc), st), "taylor_prepare")
+    d_t = torch.as_tensor(times, device=dev)
+    order = torch.as_tensor(np.argsort(-times, kind="stable").astype(np.int32), device=dev)
+    _lib.check(lib.cevb_expm_plan(_lib.ptr(ws.norms), _lib.ptr(d_t), B, E, B * E, _lib.ptr(ws.slot),
+                                  _lib.ptr(ws.worklist), _lib.ptr(ws.work_s), _lib.ptr(ws.work_count),
+                                  st), "plan")
+    ws.P.fill_(float("nan"))
+    _lib.check(lib.cevb_taylor_matrices(_lib.ptr(ws.tc), _lib.ptr(ws.norms), _lib.ptr(d_t),
+                                        _lib.ptr(order), B, E, n, _lib.ptr(ws.slot), _lib.ptr(ws.work_s),
+                                        _lib.ptr(ws.work_count), B * E, _lib.ptr(ws.P),
+                                        _lib.ptr(ws.counter), _lib.ptr(ws.nan_count), st), "matrices")
+    torch.cuda.synchronize()
+    cnt = int(ws.work_count[0])
+    return (ws.P[:cnt, :, :n].cpu().numpy(), ws.slot.cpu().numpy(), ws.work_s[:cnt].cpu().numpy(),
+            int(ws.nan_count[0]))
+
+
+@pytest.mark.parametrize("N", [35, 100, 111])
+def test_series_squaring_matrices_match_oracle(N):
+    """Pairs beyond the 5.4 switch-over: series at t 2^-s, s squarings, post-processing."""
+    from chromevol_enhanced_b200 import synthetic
+    rows = synthetic.random_param_rows(8, seed=4, linear='positive')
+    rows[:, :5] *= 4.0
+    rows[1, 8] = 5
+    times = np.array([0.0, 1e-4, 0.011, 0.06, 0.2, 0.758285, 3.0])
+    P, slot, sq, n_nan = _series_matrices(rows, times, N)
+    assert n_nan == 0
+    n_checked = 0
+    for b in range(rows.shape[0]):
+        Q = O.build_q(synthetic.row_to_dict(rows[b]), N)
+        norm1 = np.abs(Q).sum(axis=0).max()
+        for e, t in enumerate(times):
+            if t * norm1 > 5.4:
+                k = slot[b, e]
+                assert k >= 0
+                assert sq[k] == int(np.ceil(np.log2(t * norm1 / 5.4)))
+                ref = O.transition_probabilities(Q, t)
+                assert np.abs(P[k] - ref).max() <= 1e-12, (b, t, t * norm1, sq[k])
+                n_checked += 1
+            else:
+                assert slot[b, e] == -1
+    assert n_checked >= 20
+
+
+def test_large_order_falls_back_to_pade_squaring():
+    """n = 257: two matrices do not fit in shared memory, so the fused engine routes the pairs
+    that need squarings to the Pade kernel."""
+    from chromevol_enhanced_b200 import _lib, synthetic
+    from chromevol_enhanced_b200.engine import LikelihoodEngine
+    from chromevol_enhanced_b200.flatten import FlatTree
+    assert _lib.load().cevb_taylor_matrices_supported(101) == 1
+    assert _lib.load().cevb_taylor_matrices_supported(257) == 0
+    tree = synthetic.random_tree(30, seed=41, mean_len=0.15)
+    counts = synthetic.simulate_tip_counts(tree, 256, seed=42, root_state=40)
+    rows = synthetic.random_param_rows(3, seed=43, linear='positive')
+    rows[:, 7] *= 0.1
+    flat = FlatTree(tree, counts, 256)
+    eng = LikelihoodEngine(flat, path="fused")
+    assert eng.squaring == "pade"
+    a = eng.log_likelihood(rows).cpu().numpy()
+    for b in range(rows.shape[0]):
+        ref, _, _ = O.log_likelihood(tree, counts, 256, synthetic.row_to_dict(rows[b]))
+        assert a[b] == pytest.approx(ref, rel=1e-9), b
+
+
+def test_series_squaring_overflow_falls_back_to_identity():
+    """Optimiser bound corner with linear_rate = -1: expm overflows, the reference finds NaN
+    after renormalising and returns the identity (AR:156-159)."""
+    from chromevol_enhanced_b200 import synthetic
+    row = synthetic.default_param_row()
+    row[:8] = [10, 10, 10, 10, 10, 10, 10, -1.0]
+    times = np.array([0.05, 0.758])
+    P, slot, sq, n_nan = _series_matrices(row, times, 100)
+    Q = O.build_q(synthetic.row_to_dict(row), 100)
+    for e, t in enumerate(times):
+        ref = O.transition_probabilities(Q, t)
+        k = slot[0, e]
+        assert k >= 0
+        if np.array_equal(ref, np.eye(101)):
+            assert np.array_equal(P[k], np.eye(101))
+        else:
+            scale = max(1.0, np.abs(O.raw_expm(Q, t)).max())
+            assert np.abs(P[k] - ref).max() <= 1e-12 * scale
+    assert n_nan >= 1
+
+
+@pytest.mark.parametrize("squaring", ["series", "pade"])
+def test_fused_engine_squaring_variants_agree(squaring):
+    from chromevol_enhanced_b200 import synthetic
+    from chromevol_enhanced_b200.engine import LikelihoodEngine
+    from chromevol_enhanced_b200.flatten import FlatTree
+    tree = synthetic.random_tree(120, seed=21, mean_len=0.2)
+    counts = synthetic.simulate_tip_counts(tree, 50, seed=22)
+    rows = synthetic.random_param_rows(10, seed=23, linear='mixed', corners=2)
+    rows[:, :5] *= 2.0
+    flat = FlatTree(tree, counts, 50)
+    eng = LikelihoodEngine(flat, path="fused", squaring=squaring)
+    a = eng.log_likelihood(rows).cpu().numpy()
+    for b in range(rows.shape[0]):
+        ref, _, resc = O.log_likelihood(tree, counts, 50, synthetic.row_to_dict(rows[b]))
+        if np.isfinite(ref):
+            assert a[b] == pytest.approx(ref, rel=1e-9), b
+        else:
+            assert a[b] == ref or (np.isnan(a[b]) and np.isnan(ref))
+        assert int(eng.rescale_counts[b]) == resc
 
 
 def test_fused_and_materialised_paths_agree_on_config3_batch():

@@ -59,5 +59,38 @@ def raw(path, flt=None):
                 print(f"   {k:80s} {r[hdr.index(k)]:>16s} {units[hdr.index(k)]}")
 
 
+def source(path, which="0", top="25"):
+    """Stall-reason totals and the hottest SASS lines of kernel number `which` in a
+    `--page source --csv` export."""
+    csv.field_size_limit(10 ** 9)
+    rows = list(csv.reader(open(path)))
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    k = int(which)
+    lo = starts[k]
+    hi = starts[k + 1] if k + 1 < len(starts) else len(rows)
+    print("==", rows[lo][1])
+    hdr = rows[lo + 1]
+    body = [r for r in rows[lo + 2:hi] if len(r) == len(hdr)]
+    si = hdr.index("# Samples")
+    stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+    tot = collections.Counter()
+    for r in body:
+        for i, h in stall_cols:
+            tot[h] += int(r[i] or 0)
+    allsamp = sum(int(r[si] or 0) for r in body)
+    print("total samples", allsamp)
+    for h, v in tot.most_common(10):
+        print(f"   {h:28s} {v:8d} {100.0 * v / max(allsamp, 1):5.1f}%")
+    ie = hdr.index("Instructions Executed")
+    print("hottest SASS lines (samples, executed, dominant stall, instruction)")
+    for r in sorted(body, key=lambda r: -int(r[si] or 0))[:int(top)]:
+        dom = max(stall_cols, key=lambda c: int(r[c[0]] or 0))[1]
+        print(f"   {int(r[si] or 0):7d} {r[ie]:>10s} {dom:22s} {r[1].strip()[:90]}")
+    ops = collections.Counter()
+    for r in body:
+        ops[r[1].split()[0] if r[1].split() else "?"] += int(r[ie] or 0)
+    print("executed warp instructions by opcode:", ", ".join(f"{k}={v}" for k, v in ops.most_common(14)))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](*sys.argv[2:])
+    {"launches": launches, "raw": raw, "source": source}[sys.argv[1]](*sys.argv[2:])
