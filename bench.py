@@ -292,8 +292,8 @@ def run_ours(args):
     t_stage = {k: v * 1e-3 / steps for k, v in stage_ms.items()}
     apply_s, combine_s = t_stage.get("apply", 0.0), t_stage.get("combine", 0.0)
     expm_s, prep_s, init_s = t_stage.get("expm", 0.0), t_stage.get("prepare", 0.0), t_stage.get("init", 0.0)
-    levels = int(np.count_nonzero(np.diff(flat.level_off)))
-    apply_launches = max(n_chunks * levels, 1)
+    apply_launches = max(n_chunks * (int(flat.leaf_child.size > 0) +
+                                     int(np.count_nonzero(np.diff(flat.level_child_off)))), 1)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)

@@ -49,7 +49,7 @@ _PROTOTYPES = {
     "cevb_prune_fused": (_c.c_int, [c_dp, c_dp, c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                     _c.c_int, c_dp, _c.POINTER(_c.c_int32), _c.c_int, c_dp, c_dp,
                                     c_dp, c_dp, c_dp, _c.POINTER(_c.c_int32),
-                                    _c.POINTER(_c.c_int32), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                    c_dp, _c.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                     c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     "cevb_prune": (_c.c_int, [c_dp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, c_dp,
                               _c.POINTER(_c.c_int32), _c.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,

@@ -30,7 +30,7 @@ def pade_flops(n, s):
     return (2.0 * (6 + np.asarray(s, dtype=np.float64)) + 8.0 / 3.0) * float(n) ** 3
 
 
-def fused_work(flat, norm1, groups_per_warp=2):
+def fused_work(flat, norm1, groups_per_warp=1):
     """Work of the fused path for parameter vectors with ||Q||_1 = norm1[b].
 
     algorithmic flops per fused (vector, branch): 2 n^2 ncoef (the series contraction) + 3 n^2
@@ -40,24 +40,32 @@ def fused_work(flat, norm1, groups_per_warp=2):
     n = flat.n_states
     npad = (n + 7) // 8 * 8
     norm1 = np.asarray(norm1, dtype=np.float64)
-    t = flat.dist_eff[flat.level_child]                       # (branches,) in launch order
-    eta = norm1[:, None] * t[None, :]
-    ident = ~(t > 0.0)
-    mat = (~ident)[None, :] & ~(eta <= THETA)
-    fused = (~ident)[None, :] & ~mat
-    nc = np.where(fused, taylor_ncoef(np.where(fused, eta, 0.0)), 0)
-    kc = (nc + 3) // 4
-    alg = float(np.sum(fused * (2.0 * n * n * nc + 3.0 * n * n)))
+    lists = [flat.leaf_child] + [flat.level_child[flat.level_child_off[lv]:flat.level_child_off[lv + 1]]
+                                 for lv in range(len(flat.level_child_off) - 1)]
     per_warp = 8 * groups_per_warp
-    dmma = 0.0
-    off = flat.level_child_off
-    for lv in range(len(off) - 1):
-        blk = kc[:, off[lv]:off[lv + 1]]
-        pad = (-blk.shape[1]) % per_warp
+    alg = dmma = 0.0
+    n_fused = n_mat = n_ident = 0
+    nc_sum = 0.0
+    for items in lists:                                   # one launch each, in this order
+        if len(items) == 0:
+            continue
+        t = flat.dist_eff[items]
+        eta = norm1[:, None] * t[None, :]
+        ident = ~(t > 0.0)
+        mat = (~ident)[None, :] & ~(eta <= THETA)
+        fused = (~ident)[None, :] & ~mat
+        nc = np.where(fused, taylor_ncoef(np.where(fused, eta, 0.0)), 0)
+        kc = (nc + 3) // 4
+        alg += float(np.sum(fused * (2.0 * n * n * nc + 3.0 * n * n)))
+        pad = (-kc.shape[1]) % per_warp
         if pad:
-            blk = np.concatenate([blk, np.zeros((blk.shape[0], pad), dtype=blk.dtype)], axis=1)
-        wk = blk.reshape(blk.shape[0], -1, per_warp).max(axis=2)
+            kc = np.concatenate([kc, np.zeros((kc.shape[0], pad), dtype=kc.dtype)], axis=1)
+        wk = kc.reshape(kc.shape[0], -1, per_warp).max(axis=2)
         dmma += float(wk.sum()) * groups_per_warp * n * (npad // 8) * 512.0
-    return {"algorithmic_flops": alg, "dmma_flops": dmma, "fused_pairs": int(fused.sum()),
-            "materialised_pairs": int(mat.sum()), "identity_pairs": int(ident.sum()) * norm1.shape[0],
-            "mean_ncoef": float(nc[fused].mean()) if fused.any() else 0.0}
+        n_fused += int(fused.sum())
+        n_mat += int(mat.sum())
+        n_ident += int(ident.sum()) * norm1.shape[0]
+        nc_sum += float(nc[fused].sum())
+    return {"algorithmic_flops": alg, "dmma_flops": dmma, "fused_pairs": n_fused,
+            "materialised_pairs": n_mat, "identity_pairs": n_ident,
+            "mean_ncoef": nc_sum / max(n_fused, 1)}

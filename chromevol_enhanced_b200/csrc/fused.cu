@@ -951,7 +951,7 @@ extern "C" int cevb_prune_fused(const double* tc, const double* norms, const dou
                                 int n_levels, const int32_t* child_off, const int32_t* child_idx,
                                 const int32_t* branch_of, const int32_t* leaf_code,
                                 const int32_t* level_child, const int32_t* level_child_off_host,
-                                const int32_t* level_child_nleaf_host, const double* t_node,
+                                const int32_t* leaf_child, int n_leaf_child, const double* t_node,
                                 const double* root_freq, double* node_vec, double* w, double* wr,
                                 uint8_t* mode, double* logl, int32_t* rescales,
                                 int level_begin, int level_end, int stages, void* stream) {
@@ -969,6 +969,12 @@ extern "C" int cevb_prune_fused(const double* tc, const double* norms, const dou
         leaf_init_fused_kernel<<<lgrid, 128, 0, st>>>(n, ldp, n_nodes, leaf_code, node_vec);
         CEVB_CHECK_LAUNCH("leaf_init_kernel");
     }
+    if (stages & CEVB_FUSED_LEAVES) {
+        // branches above observed leaves depend on nothing below them: all levels in one launch
+        const int rc = launch_apply(tc, norms, B, n, n_nodes, leaf_child, n_leaf_child, 1, t_node,
+                                    leaf_code, node_vec, w, wr, mode, st);
+        if (rc != 0) return rc;
+    }
     const size_t csmem = 2 * (size_t)n * sizeof(double);
     if (level_begin < 0) level_begin = 0;
     if (level_end > n_levels) level_end = n_levels;
@@ -976,14 +982,9 @@ extern "C" int cevb_prune_fused(const double* tc, const double* norms, const dou
         const int cnt = level_off_host[lv + 1] - level_off_host[lv];
         if (cnt <= 0) continue;
         if (stages & CEVB_FUSED_APPLY) {
-            // observed-leaf children first (one-hot child vectors), then the others
             const int c0 = level_child_off_host[lv], c1 = level_child_off_host[lv + 1];
-            const int nl = level_child_nleaf_host ? level_child_nleaf_host[lv] : 0;
-            int rc = launch_apply(tc, norms, B, n, n_nodes, level_child + c0, nl, 1, t_node, leaf_code,
-                                  node_vec, w, wr, mode, st);
-            if (rc != 0) return rc;
-            rc = launch_apply(tc, norms, B, n, n_nodes, level_child + c0 + nl, c1 - c0 - nl, 0, t_node,
-                              leaf_code, node_vec, w, wr, mode, st);
+            const int rc = launch_apply(tc, norms, B, n, n_nodes, level_child + c0, c1 - c0, 0, t_node,
+                                        leaf_code, node_vec, w, wr, mode, st);
             if (rc != 0) return rc;
         }
         if (stages & CEVB_FUSED_COMBINE) {

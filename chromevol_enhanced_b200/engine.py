@@ -25,7 +25,7 @@ from .flatten import FlatTree
 PARAM_ORDER = ['gain', 'loss', 'dupl', 'demidupl_gain', 'demidupl_loss',
                'base_number_gain', 'base_number_loss', 'linear_rate', 'base_number']
 
-FUSED_INIT, FUSED_APPLY, FUSED_COMBINE, FUSED_ALL = 1, 2, 4, 7
+FUSED_INIT, FUSED_APPLY, FUSED_COMBINE, FUSED_LEAVES, FUSED_ALL = 1, 2, 4, 8, 15
 INFO_IDENTITY_T0 = 1
 INFO_NAN_FALLBACK = 2
 INFO_GROWTH = 4
@@ -125,7 +125,7 @@ class LikelihoodEngine:
         self.h_level_off = np.ascontiguousarray(flat.level_off, dtype=np.int32)
         self.d_level_child = torch.as_tensor(flat.level_child, **i32)
         self.h_level_child_off = np.ascontiguousarray(flat.level_child_off, dtype=np.int32)
-        self.h_level_child_nleaf = np.ascontiguousarray(flat.level_child_nleaf, dtype=np.int32)
+        self.d_leaf_child = torch.as_tensor(flat.leaf_child, **i32)
         self.d_t_node = torch.as_tensor(flat.dist_eff, dtype=torch.float64, device=self.device)
         self.d_t_order = torch.as_tensor(np.argsort(-np.nan_to_num(flat.t_unique), kind="stable")
                                          .astype(np.int32), device=self.device)
@@ -259,8 +259,7 @@ class LikelihoodEngine:
                 _lib.ptr(self.d_child_off), _lib.ptr(self.d_child_idx), _lib.ptr(self.d_branch_of),
                 _lib.ptr(self.d_leaf_code), _lib.ptr(self.d_level_child),
                 self.h_level_child_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
-                self.h_level_child_nleaf.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
-                _lib.ptr(self.d_t_node), _lib.ptr(d_root_freq), _lib.ptr(self._node_vec),
+                _lib.ptr(self.d_leaf_child), int(f.leaf_child.size), _lib.ptr(self.d_t_node), _lib.ptr(d_root_freq), _lib.ptr(self._node_vec),
                 _lib.ptr(ws.w), _lib.ptr(ws.wr), _lib.ptr(ws.mode), _lib.ptr(self._logl), _lib.ptr(self._rescales),
                 lo, hi, stages, st), "cevb_prune_fused")
 
@@ -270,6 +269,8 @@ class LikelihoodEngine:
             # same launches, issued level by level so the two kernels can be timed separately
             prune(0, 0, FUSED_INIT)
             ev = self._mark("init", e2)
+            prune(0, 0, FUSED_LEAVES)
+            ev = self._mark("apply", ev)
             for lv in range(f.n_levels):
                 prune(lv, lv + 1, FUSED_APPLY)
                 ev = self._mark("apply", ev)
@@ -308,9 +309,8 @@ class LikelihoodEngine:
         levels = int(np.count_nonzero(np.diff(self.flat.level_off)))
         if self.path != "fused":
             return 9 + levels
-        nl = self.flat.level_child_nleaf
-        tot = np.diff(self.flat.level_child_off)
-        applies = int(np.count_nonzero(nl)) + int(np.count_nonzero(tot - nl))
+        applies = int(self.flat.leaf_child.size > 0) + \
+            int(np.count_nonzero(np.diff(self.flat.level_child_off)))
         return (7 if self.squaring == "series" else 12) + levels + applies
 
     # ------------------------------------------------------------------ public

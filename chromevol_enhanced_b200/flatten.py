@@ -100,26 +100,24 @@ class FlatTree:
         self.level_off = level_off
         self.n_levels = n_levels
 
-        # branches grouped by the level of their PARENT (the fused kernel handles one level's
-        # branches per launch): observed-leaf children first (their one-hot vectors need no
-        # staging), and inside each part longest first so that 8-branch groups need similar
-        # series lengths
+        # Work lists of the fused kernels.  Branches above observed leaves depend on nothing
+        # below them, so all of them (every level) form one list; the remaining branches
+        # (internal or missing-data children) are grouped by the level of their PARENT, one
+        # launch per level.  Longest first inside each list, so that the 8-branch groups of the
+        # tensor-core kernel need similar series lengths.
+        tkey = lambda c: -(eff[c] if eff[c] == eff[c] else 0.0)
+        self.leaf_child = np.asarray(sorted((c for c in range(1, n_nodes) if leaf_code[c] >= 0),
+                                            key=tkey), dtype=np.int32)
         lvl_child = []
         lvl_child_off = [0]
-        lvl_child_nleaf = []
-        tkey = lambda c: -(eff[c] if eff[c] == eff[c] else 0.0)
         for lv in range(n_levels):
             kids = []
             for p in self.level_nodes[level_off[lv]:level_off[lv + 1]]:
                 kids.extend(self.child_idx[child_off[p]:child_off[p + 1]].tolist())
-            obs = sorted((c for c in kids if leaf_code[c] >= 0), key=tkey)
-            rest = sorted((c for c in kids if leaf_code[c] < 0), key=tkey)
-            lvl_child.extend(obs + rest)
+            lvl_child.extend(sorted((c for c in kids if leaf_code[c] < 0), key=tkey))
             lvl_child_off.append(len(lvl_child))
-            lvl_child_nleaf.append(len(obs))
         self.level_child = np.asarray(lvl_child, dtype=np.int32)
         self.level_child_off = np.asarray(lvl_child_off, dtype=np.int32)
-        self.level_child_nleaf = np.asarray(lvl_child_nleaf, dtype=np.int32)
 
         # pre-order (parents before children, children in file order) for the simulator (AR:551)
         pre = []

@@ -49,7 +49,8 @@ extern "C" {
 #define CEVB_FUSED_INIT 1
 #define CEVB_FUSED_APPLY 2
 #define CEVB_FUSED_COMBINE 4
-#define CEVB_FUSED_ALL 7
+#define CEVB_FUSED_LEAVES 8
+#define CEVB_FUSED_ALL 15
 #define CEVB_TAYLOR_THETA 5.4   /* t ||Q||_1 up to which expm(Q t) is summed without squaring     */
 
 /* norms[b][.] */
@@ -151,25 +152,26 @@ int cevb_taylor_apply(const double* tc, const double* norms, int B, int n, int n
                       uint8_t* mode, void* stream);
 
 /* Whole tree with the fused path: same contract and tree arrays as cevb_prune, plus
- *   level_child [n_branches]  child nodes grouped by the level of their parent (any order
- *                             inside a level; longest branches first packs the work best),
+ *   leaf_child [n_leaf_child] every non-root node that is an observed leaf (leaf_code >= 0):
+ *                             their branches need no child vector and go in one launch,
+ *   level_child [..]          the remaining child nodes (internal, missing data) grouped by the
+ *                             level of their parent (any order inside a level; longest
+ *                             branches first packs the work best),
  *   level_child_off [n_levels+1] HOST offsets into level_child,
- *   level_child_nleaf [n_levels] HOST: the first level_child_nleaf[lv] children of level lv
- *                             are observed leaves (may be NULL = unknown),
  *   t_node [n_nodes]          effective branch length above every node,
  *   P / slot                  materialised matrices and slot map from cevb_expm_plan +
  *                             cevb_expm_branches_list (E = row length of slot),
  *   w, wr [B][n_nodes][ldp], mode [B][n_nodes]   scratch.
  * Levels [level_begin, level_end) are processed; `stages` is a mask of CEVB_FUSED_INIT (zero
- * mode / rescales, write the leaf vectors), CEVB_FUSED_APPLY and CEVB_FUSED_COMBINE.  The whole
- * tree in one call is (0, n_levels, CEVB_FUSED_ALL); the split form lets a caller time the two
- * kernels of a level separately. */
+ * mode / rescales, write the leaf vectors), CEVB_FUSED_LEAVES (the leaf_child launch),
+ * CEVB_FUSED_APPLY and CEVB_FUSED_COMBINE.  The whole tree in one call is (0, n_levels,
+ * CEVB_FUSED_ALL); the split form lets a caller time the kernels separately. */
 int cevb_prune_fused(const double* tc, const double* norms, const double* P, const int32_t* slot,
                      int B, int E, int n, int n_nodes, int root, const int32_t* level_nodes,
                      const int32_t* level_off_host, int n_levels, const int32_t* child_off,
                      const int32_t* child_idx, const int32_t* branch_of, const int32_t* leaf_code,
                      const int32_t* level_child, const int32_t* level_child_off_host,
-                     const int32_t* level_child_nleaf_host, const double* t_node,
+                     const int32_t* leaf_child, int n_leaf_child, const double* t_node,
                      const double* root_freq, double* node_vec, double* w, double* wr,
                      uint8_t* mode, double* logl, int32_t* rescales, int level_begin, int level_end,
                      int stages, void* stream);
