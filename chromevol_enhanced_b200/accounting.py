@@ -4,25 +4,43 @@ from __future__ import annotations
 
 import numpy as np
 
-THETA = 5.4          # CEVB_TAYLOR_THETA
 KC = 10              # CEVB_TAYLOR_KC
 
 
-def taylor_ncoef(eta):
+def taylor_ncoef(x, mut):
     """Vectorised copy of the device rule (csrc/fused.cu: taylor_ncoef): series coefficients
-    (degree + 1) for eta = t ||Q||_1."""
-    eta = np.asarray(eta, dtype=np.float64)
-    out = np.full(eta.shape, 4 * KC, dtype=np.int64)
-    done = ~(eta > 0.0)
+    (degree + 1) for x = nu t, mut = mu t; 4*KC + 1 when the table is too short."""
+    x = np.asarray(x, dtype=np.float64)
+    mut = np.broadcast_to(np.asarray(mut, dtype=np.float64), x.shape)
+    out = np.full(x.shape, 4 * KC + 1, dtype=np.int64)
+    done = ~(x > 0.0)
     out[done] = 1
-    term = eta.copy()
+    term = x.copy()
     with np.errstate(all='ignore'):
-        for k in range(1, 4 * KC - 1):
-            term = term * (eta / (k + 1))
-            ok = (~done) & ((k + 2) > eta) & (term / (1.0 - eta / (k + 2)) <= 1e-18)
+        sc = np.exp(-mut)
+        for k in range(1, 4 * KC):
+            term = term * (x / (k + 1))
+            ok = (~done) & ((k + 2) > x) & (term / (1.0 - x / (k + 2)) * sc <= 1e-18)
             out[ok] = k + 1
             done |= ok
     return out
+
+
+def plan_pairs(t, nu, mu):
+    """(kind, ncoef, squarings) per (vector, branch): kind 0 fused, 1 identity, 2 materialised."""
+    t = np.asarray(t, dtype=np.float64)[None, :]
+    x = np.asarray(nu, dtype=np.float64)[:, None] * t
+    mut = np.asarray(mu, dtype=np.float64)[:, None] * t
+    ident = np.broadcast_to(~(t > 0.0), x.shape)
+    nc = taylor_ncoef(x, mut)
+    s = np.zeros(x.shape, dtype=np.int64)
+    need = (nc > 4 * KC) & ~ident
+    while need.any():
+        s[need] += 1
+        nc[need] = taylor_ncoef(x[need] / 2.0 ** s[need], mut[need] / 2.0 ** s[need])
+        need = (nc > 4 * KC) & ~ident & (s < 1000)
+    kind = np.where(ident, 1, np.where(s > 0, 2, 0))
+    return kind, nc, s
 
 
 def pade_flops(n, s):
@@ -30,8 +48,8 @@ def pade_flops(n, s):
     return (2.0 * (6 + np.asarray(s, dtype=np.float64)) + 8.0 / 3.0) * float(n) ** 3
 
 
-def fused_work(flat, norm1, groups_per_warp=1):
-    """Work of the fused path for parameter vectors with ||Q||_1 = norm1[b].
+def fused_work(flat, nu, mu, groups_per_warp=1):
+    """Work of the fused path for parameter vectors with shifted norm nu[b] and shift mu[b].
 
     algorithmic flops per fused (vector, branch): 2 n^2 ncoef (the series contraction) + 3 n^2
     (floor/row sum/dot product); executed DMMA flops follow the kernel's grouping (a warp owns
@@ -39,7 +57,8 @@ def fused_work(flat, norm1, groups_per_warp=1):
     them, on rows padded to 8 columns)."""
     n = flat.n_states
     npad = (n + 7) // 8 * 8
-    norm1 = np.asarray(norm1, dtype=np.float64)
+    nu = np.asarray(nu, dtype=np.float64)
+    mu = np.asarray(mu, dtype=np.float64)
     lists = [flat.leaf_child] + [flat.level_child[flat.level_child_off[lv]:flat.level_child_off[lv + 1]]
                                  for lv in range(len(flat.level_child_off) - 1)]
     per_warp = 8 * groups_per_warp
@@ -49,12 +68,9 @@ def fused_work(flat, norm1, groups_per_warp=1):
     for items in lists:                                   # one launch each, in this order
         if len(items) == 0:
             continue
-        t = flat.dist_eff[items]
-        eta = norm1[:, None] * t[None, :]
-        ident = ~(t > 0.0)
-        mat = (~ident)[None, :] & ~(eta <= THETA)
-        fused = (~ident)[None, :] & ~mat
-        nc = np.where(fused, taylor_ncoef(np.where(fused, eta, 0.0)), 0)
+        kind, nc, _ = plan_pairs(flat.dist_eff[items], nu, mu)
+        fused, mat, ident = kind == 0, kind == 2, kind == 1
+        nc = np.where(fused, nc, 0)
         kc = (nc + 3) // 4
         alg += float(np.sum(fused * (2.0 * n * n * nc + 3.0 * n * n)))
         pad = (-kc.shape[1]) % per_warp
@@ -64,7 +80,7 @@ def fused_work(flat, norm1, groups_per_warp=1):
         dmma += float(wk.sum()) * groups_per_warp * n * (npad // 8) * 512.0
         n_fused += int(fused.sum())
         n_mat += int(mat.sum())
-        n_ident += int(ident.sum()) * norm1.shape[0]
+        n_ident += int(ident.sum())
         nc_sum += float(nc[fused].sum())
     return {"algorithmic_flops": alg, "dmma_flops": dmma, "fused_pairs": n_fused,
             "materialised_pairs": n_mat, "identity_pairs": n_ident,

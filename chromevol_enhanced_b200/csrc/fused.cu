@@ -30,48 +30,99 @@ namespace cevb {
 
 constexpr int F_KC = CEVB_TAYLOR_KC;       // chunks of 4 series coefficients (degrees 0..39)
 constexpr int F_JT = 13;                   // 8-column tiles per pass (104 columns)
-constexpr double F_THETA = CEVB_TAYLOR_THETA;
 
-// number of series coefficients (degree + 1) needed for eta = t ||Q||_1
-__host__ __device__ inline int taylor_ncoef(double eta) {
-    if (!(eta > 0.0)) return 1;
-    double term = eta;  // eta^k / k!
-    int k = 1;
-    for (; k < 4 * F_KC - 1; ++k) {
-        term *= eta / (double)(k + 1);  // eta^(k+1) / (k+1)!
-        if ((double)(k + 2) > eta && term / (1.0 - eta / (double)(k + 2)) <= 1e-18) break;
+// The series is summed for the SHIFTED matrix (uniformisation): with mu = max(0, -min_i Q_ii),
+//     expm(Q t) = e^{-mu t} sum_k t^k C_k,   C_k = (Q + mu I)^k / k!.
+// For a generator Q + mu I is entrywise non-negative, so the sum has no cancellation and its
+// norm nu = min(||Q + mu I||_1, ||Q + mu I||_inf) is about half of ||Q||_1.
+// Number of series coefficients (degree + 1) so that the truncation bound
+//     x^(K+1)/(K+1)! / (1 - x/(K+2)) * e^{-mu t} <= 1e-18,   x = nu t;
+// a result above 4 * F_KC means the coefficient table is too short (scale and square).
+__host__ __device__ inline int taylor_ncoef(double x, double mut) {
+    if (!(x > 0.0)) return 1;
+    const double sc = exp(-mut);
+    double term = x;  // x^k / k!
+    for (int k = 1; k < 4 * F_KC; ++k) {
+        term *= x / (double)(k + 1);  // x^(k+1) / (k+1)!
+        if ((double)(k + 2) > x && term / (1.0 - x / (double)(k + 2)) * sc <= 1e-18) return k + 1;
     }
-    return k + 1;
+    return 4 * F_KC + 1;
 }
 
-// squarings for eta > theta: smallest s with eta 2^-s <= theta (non-finite eta -> 0; the series
-// is then evaluated at NaN and the post-processing falls back to the identity, AR:156-159)
-__host__ __device__ inline int taylor_squarings(double eta) {
-    int s = 0;
-    while (eta > F_THETA && eta < INFINITY && s < 1000) {
-        eta *= 0.5;
-        ++s;
+// what to do with one (vector, branch length) pair
+struct PairPlan {
+    int nc;      // series coefficients (0: nothing to sum)
+    int s;       // squarings (> 0 or non-finite rates: the matrix has to be materialised)
+    int kind;    // 0 fused series, 1 identity (t == 0), 2 materialised
+    double tau;  // t 2^-s
+    double a0;   // e^{-mu tau}
+};
+
+__host__ __device__ inline PairPlan plan_pair(double t, double nu, double mu) {
+    PairPlan p = {0, 0, 0, 0.0, 1.0};
+    if (!(t > 0.0)) {  // t == 0 -> identity (AR:146-148); t < 0 / NaN never reach here
+        p.kind = 1;
+        return p;
     }
-    return s;
+    const double x = t * nu, mut = t * mu;
+    if (!(x < INFINITY) || !(mut < INFINITY)) {
+        // NaN / inf rates: the series is evaluated at NaN and the post-processing falls back to
+        // the identity like the reference does (AR:156-166)
+        p.kind = 2;
+        p.nc = 4;
+        p.tau = NAN;
+        p.a0 = NAN;
+        return p;
+    }
+    int s = 0;
+    int nc = taylor_ncoef(x, mut);
+    while (nc > 4 * F_KC && s < 1000) {
+        ++s;
+        nc = taylor_ncoef(ldexp(x, -s), ldexp(mut, -s));
+    }
+    p.nc = nc;
+    p.s = s;
+    p.kind = s > 0 ? 2 : 0;
+    p.tau = ldexp(t, -s);
+    p.a0 = exp(-ldexp(mut, -s));
+    return p;
 }
 
 // ---------------------------------------------------------------------------------------------
-// ||Q||_1 and the compressed column structure of Q (row indices of the non-zeros of every
-// column), one CTA per parameter vector, one thread per column.
+// ||Q||_1, the shift mu = max(0, -min_i Q_ii), nu = min(||Q + mu I||_1, ||Q + mu I||_inf) and the
+// compressed column structure of Q (row indices of the non-zeros of every column); one CTA per
+// parameter vector, one thread per column / row.
 __global__ void __launch_bounds__(128) q_structure_kernel(const double* __restrict__ pw, int n,
                                                           int ldq, double* __restrict__ norms,
                                                           uint16_t* __restrict__ csc,
                                                           uint8_t* __restrict__ csc_cnt) {
     __shared__ double red[4];
+    __shared__ double s_mu;
     const int b = blockIdx.x, tid = threadIdx.x;
     const double* Q = pw + (size_t)b * CEVB_NPOW * n * ldq;
     uint16_t* idx_c = csc + (size_t)b * 2 * CEVB_MAX_SPARSE * n;
     uint8_t* cnt_c = csc_cnt + (size_t)b * 2 * n;
-    double best = 0.0;
+    auto block_max = [&](double v) {
+        v = warp_max(v);
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        __syncthreads();
+        return fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
+    };
+    // shift
+    double dmax = 0.0;
     bool nan = false;
     for (int j = tid; j < n; j += 128) {
+        const double d = Q[(size_t)j * ldq + j];
+        if (d != d) nan = true;
+        dmax = fmax(dmax, -d);
+    }
+    const double mu = block_max(dmax);
+    // column pass: structure, ||Q||_1, ||Q + mu I||_1
+    double best = 0.0, best_s = 0.0;
+    for (int j = tid; j < n; j += 128) {
         int cc = 0;
-        double sum = 0.0;
+        double sum = 0.0, sum_s = 0.0;
         for (int i = 0; i < n; ++i) {
             const double q = Q[(size_t)i * ldq + j];
             if (q != 0.0) {  // NaN != 0 is true: kept as "non-zero"
@@ -79,28 +130,44 @@ __global__ void __launch_bounds__(128) q_structure_kernel(const double* __restri
                 ++cc;
             }
             sum += fabs(q);
+            sum_s += fabs(i == j ? q + mu : q);
         }
         cnt_c[j] = (cc > CEVB_MAX_SPARSE) ? 255 : (uint8_t)cc;
         if (sum != sum) nan = true;
         best = fmax(best, sum);
+        best_s = fmax(best_s, sum_s);
     }
-    best = warp_max(best);
+    // row pass: ||Q + mu I||_inf
+    double best_r = 0.0;
+    for (int i = tid; i < n; i += 128) {
+        double sum_s = 0.0;
+        for (int j = 0; j < n; ++j) {
+            const double q = Q[(size_t)i * ldq + j];
+            sum_s += fabs(i == j ? q + mu : q);
+        }
+        best_r = fmax(best_r, sum_s);
+    }
+    const double one = block_max(best);
+    const double nu1 = block_max(best_s);
+    const double nui = block_max(best_r);
     const bool anynan = __syncthreads_or(nan);
-    if ((tid & 31) == 0) red[tid >> 5] = best;
-    __syncthreads();
     if (tid == 0) {
-        const double m = fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
-        norms[(size_t)b * CEVB_NNORM + CEVB_NORM_ONE] = anynan ? NAN : m;   // numpy max propagates NaN
+        double* out = norms + (size_t)b * CEVB_NNORM;
+        out[CEVB_NORM_ONE] = anynan ? NAN : one;   // numpy max propagates NaN
+        out[CEVB_NORM_SHIFT] = anynan ? NAN : mu;
+        out[CEVB_NORM_SHIFTED] = anynan ? NAN : fmin(nu1, nui);
     }
+    (void)s_mu;
 }
 
 // ---------------------------------------------------------------------------------------------
-// C_0 = I, C_k = C_{k-1} Q / k, one CTA per (row i, vector b); row i of C_k only needs row i of
-// C_{k-1}.  Output layout tc[b][i][c][j][4]: chunk c holds degrees 4c..4c+3 interleaved per
+// C_0 = I, C_k = C_{k-1} (Q + mu I) / k, one CTA per (row i, vector b); row i of C_k only needs
+// row i of C_{k-1}.  Output layout tc[b][i][c][j][4]: chunk c holds degrees 4c..4c+3 interleaved per
 // column, exactly the B-operand fragment order of DMMA (lane 4g+t <- column g, degree t).
 __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restrict__ pw,
                                                            const uint16_t* __restrict__ csc,
                                                            const uint8_t* __restrict__ csc_cnt,
+                                                           const double* __restrict__ norms,
                                                            int n, int ldq, int npad,
                                                            double* __restrict__ tc) {
     extern __shared__ double shc[];
@@ -112,6 +179,7 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
     const uint16_t* idx_c = csc + (size_t)b * 2 * CEVB_MAX_SPARSE * n;
     const uint8_t* cnt_c = csc_cnt + (size_t)b * 2 * n;
     double* out = tc + ((size_t)b * n + i) * F_KC * npad * 4;
+    const double mu = norms[(size_t)b * CEVB_NNORM + CEVB_NORM_SHIFT];
     for (int j = tid; j < npad; j += 128) cur[j] = (j == i) ? 1.0 : 0.0;
     __syncthreads();
     for (int k = 0; k < 4 * F_KC; ++k) {
@@ -120,7 +188,7 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
             const double inv_den = (double)(k + 1);
             for (int j = tid; j < n; j += 128) {
                 const int cnt = cnt_c[j];
-                double acc = 0.0;
+                double acc = cur[j] * mu;
                 if (cnt == 255) {
                     for (int r = 0; r < n; ++r) acc = fma(cur[r], Q[(size_t)r * ldq + j], acc);
                 } else {
@@ -157,14 +225,14 @@ __global__ void __launch_bounds__(256) expm_plan_kernel(const double* __restrict
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M) return;
     const int b = (int)(idx / E), e = (int)(idx - (long long)b * E);
-    const double tb = t[e];
-    const double eta = tb * norms[(size_t)b * CEVB_NNORM + CEVB_NORM_ONE];
+    const double* nr = norms + (size_t)b * CEVB_NNORM;
+    const PairPlan pp = plan_pair(t[e], nr[CEVB_NORM_SHIFTED], nr[CEVB_NORM_SHIFT]);
     int s = -1;
-    if (tb > 0.0 && !(eta <= F_THETA)) {
+    if (pp.kind == 2) {
         const unsigned int q = atomicAdd(count, 1u);
         if ((long long)q < cap) {
             worklist[q] = (int32_t)idx;
-            if (work_s != nullptr) work_s[q] = taylor_squarings(eta);
+            if (work_s != nullptr) work_s[q] = pp.s;
             s = (int)q;
         } else {
             s = -2;  // overflow: the host sees count > cap and re-runs with smaller chunks
@@ -276,47 +344,41 @@ __global__ void __launch_bounds__(32 * (NW + 1)) taylor_apply_kernel(ApplyArgs a
     double* Ls = As + (size_t)(EB / 8) * F_KC * 32;                           // [EB][ldl] (not LEAF)
     double* Bs = Ls + (LEAF ? 0 : (size_t)EB * ldl);                          // ring of row tiles
 
-    const double norm1 = a.norms[(size_t)b * CEVB_NNORM + CEVB_NORM_ONE];
+    const double nu = a.norms[(size_t)b * CEVB_NNORM + CEVB_NORM_SHIFTED];
+    const double mu = a.norms[(size_t)b * CEVB_NNORM + CEVB_NORM_SHIFT];
     for (int x = tid; x < EB; x += blockDim.x) {
         const int e = e0 + x;
         int nc = 0, child = -1, code = -2;
-        double tau = 0.0;
+        double tau = 0.0, a0 = 0.0;
         if (e < a.n_items && EVAL) {
             const int item = a.items[e];
-            const double t = a.t_node[item];
-            const double eta = t * norm1;
-            if (t > 0.0 && !(eta <= F_THETA)) {
+            const PairPlan pp = plan_pair(a.t_node[item], nu, mu);
+            if (pp.kind == 2) {
                 child = a.slot[(size_t)b * a.E + item];     // P slot of this pair (< 0: overflow)
                 if (child >= 0) {
-                    const int sq = taylor_squarings(eta);
-                    if (eta < INFINITY) {
-                        tau = ldexp(t, -sq);
-                        nc = taylor_ncoef(ldexp(eta, -sq));
-                    } else {
-                        tau = NAN;   // NaN / inf rates: NaN series, identity after post-processing
-                        nc = 4;
-                    }
+                    nc = pp.nc;
+                    tau = pp.tau;
+                    a0 = pp.a0;
                 }
             }
         } else if (e < a.n_items) {
             child = a.items[e];
             code = a.leaf_code[child];
-            const double t = a.t_node[child];
-            const double eta = t * norm1;
-            if (!(t > 0.0)) {
-                a.mode[(size_t)b * a.n_nodes + child] = 1;  // t == 0 -> identity (AR:146-148)
-            } else if (!(eta <= F_THETA)) {
-                a.mode[(size_t)b * a.n_nodes + child] = 2;  // scaling-and-squaring path
+            const PairPlan pp = plan_pair(a.t_node[child], nu, mu);
+            if (pp.kind != 0) {
+                // 1: t == 0 -> identity (AR:146-148); 2: scaling-and-squaring path
+                a.mode[(size_t)b * a.n_nodes + child] = (uint8_t)pp.kind;
             } else {
-                nc = taylor_ncoef(eta);
-                tau = t;
+                nc = pp.nc;
+                tau = pp.tau;
+                a0 = pp.a0;
             }
         }
         s_child[x] = child;
         s_code[x] = code;
         s_nc[x] = nc;
         double* arow = As + (size_t)(x >> 3) * F_KC * 32 + (x & 7) * 4;
-        double p = 1.0;
+        double p = a0;  // e^{-mu tau} tau^k
         for (int k = 0; k < 4 * F_KC; ++k) {
             arow[(k >> 2) * 32 + (k & 3)] = (k < nc) ? p : 0.0;
             p *= tau;
@@ -864,8 +926,8 @@ extern "C" int cevb_taylor_prepare(const double* pw, int B, int n, double* norms
     q_structure_kernel<<<B, 128, 0, st>>>(pw, n, ldq_of(n), norms, csc, csc_cnt);
     CEVB_CHECK_LAUNCH("q_structure_kernel");
     dim3 grid(n, B);
-    taylor_coeff_kernel<<<grid, 128, sizeof(double) * 6 * (size_t)npad, st>>>(pw, csc, csc_cnt, n,
-                                                                             ldq_of(n), npad, tc);
+    taylor_coeff_kernel<<<grid, 128, sizeof(double) * 6 * (size_t)npad, st>>>(
+        pw, csc, csc_cnt, norms, n, ldq_of(n), npad, tc);
     CEVB_CHECK_LAUNCH("taylor_coeff_kernel");
     return 0;
 }

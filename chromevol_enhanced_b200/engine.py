@@ -291,7 +291,7 @@ class LikelihoodEngine:
                 cnt = int(min(int(ws.work_count[0]), ws.p_slots))
                 self.info_log.append((ws.work_s[:cnt].cpu().numpy().copy(),
                                       ws.slot[:nb].cpu().numpy().copy(),
-                                      ws.norms[:nb, 0].cpu().numpy().copy()))
+                                      ws.norms[:nb].cpu().numpy().copy()))
             return
         self._transition_matrices(ws, nb, full_pivot)
         # element-growth monitor of the tile-pivoted solve: OR into a device flag, no host sync

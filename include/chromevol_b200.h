@@ -51,7 +51,6 @@ extern "C" {
 #define CEVB_FUSED_COMBINE 4
 #define CEVB_FUSED_LEAVES 8
 #define CEVB_FUSED_ALL 15
-#define CEVB_TAYLOR_THETA 5.4   /* t ||Q||_1 up to which expm(Q t) is summed without squaring     */
 
 /* norms[b][.] */
 #define CEVB_NORM_ONE 0      /* ||Q||_1 */
@@ -61,6 +60,8 @@ extern "C" {
 #define CEVB_NORM_D10 4
 #define CEVB_NORM_ABS7 5     /* || |Q|^7 ||_1, then ^11, ^15, ^19, ^27 */
 #define CEVB_NORM_DENSE 10   /* 1.0 if some column of Q has more than CEVB_MAX_SPARSE non-zeros */
+#define CEVB_NORM_SHIFT 11   /* mu = max(0, -min_i Q_ii): the series path sums (Q + mu I)      */
+#define CEVB_NORM_SHIFTED 12 /* nu = min(||Q + mu I||_1, ||Q + mu I||_inf)                       */
 
 /* info flags (bits 16..) */
 #define CEVB_INFO_IDENTITY_T0 1   /* t == 0 -> exact identity (AR:146-148)            */
@@ -109,15 +110,21 @@ int cevb_expm_branches_list(const double* pw, const double* norms, const uint16_
                             long long work_cap, void* stream);
 
 /* ---- (2c) fused path tables.  All branches of a parameter vector share Q (AR:230-233 with no
- * branch_params), so expm(Q t) = sum_k t^k C_k with C_k = Q^k / k! formed once per vector.
- * cevb_taylor_prepare needs only slot 0 of pw (Q) and writes
- *   norms[b][CEVB_NORM_ONE] = ||Q_b||_1, the compressed-column structure csc / csc_cnt and
+ * branch_params), so with the shift mu = max(0, -min_i Q_ii) (uniformisation: Q + mu I is
+ * non-negative for a generator, so the series has no cancellation)
+ *     expm(Q t) = e^{-mu t} sum_k t^k C_k,   C_k = (Q + mu I)^k / k!
+ * with C_k formed once per vector.  cevb_taylor_prepare needs only slot 0 of pw (Q) and writes
+ *   norms[b][CEVB_NORM_ONE / _SHIFT / _SHIFTED] = ||Q_b||_1, mu_b, nu_b,
+ *   the compressed-column structure csc / csc_cnt and
  *   tc [B][n][CEVB_TAYLOR_KC][n_pad][4]   (n_pad = n rounded up to 8; cevb_taylor_doubles(n)
  *   doubles per vector); chunk c of row i holds degrees 4c..4c+3 interleaved per column.
- * cevb_expm_plan lists every (vector, branch length) pair with t ||Q||_1 > CEVB_TAYLOR_THETA,
- * which needs scaling and squaring and therefore a materialised matrix: slot [B][E] = position
- * in worklist (-1 = fused path, -2 = list overflow), work_s [cap] = squarings of that position
- * (may be NULL), *count = pairs found (may exceed cap; the caller then re-plans).
+ * The number of terms for a pair is the smallest K + 1 with
+ *     x^(K+1)/(K+1)! / (1 - x/(K+2)) e^{-mu t} <= 1e-18,  x = nu t;
+ * cevb_expm_plan lists every (vector, branch length) pair for which 40 terms do not reach
+ * that (nu t above about 7), which needs scaling and squaring and therefore a materialised
+ * matrix: slot [B][E] = position in worklist (-1 = fused path, -2 = list overflow),
+ * work_s [cap] = squarings of that position (may be NULL), *count = pairs found (may exceed
+ * cap; the caller then re-plans).
  * cevb_taylor_matrices fills the P slots of a plan: the series at t 2^-s for all listed pairs
  * of a vector at once (tensor cores, t_order = branch-length indices sorted by decreasing t),
  * then s squarings and the AR:153-159 post-processing per matrix in shared memory.

@@ -58,7 +58,17 @@ def _apply(rows, times, N, child_vectors=None, codes=None):
                "taylor_apply")
     torch.cuda.synchronize()
     w = (w / wr)[:, :, :n].cpu().numpy().reshape(B, E, K, n)          # AR:154
-    return w, mode.cpu().numpy().reshape(B, E, K), ws.norms[:, 0].cpu().numpy()
+    return w, mode.cpu().numpy().reshape(B, E, K), ws.norms.cpu().numpy()
+
+
+def _host_plan(Q, times):
+    """Host mirror of the device's per-pair decision (accounting.plan_pairs) from the oracle Q."""
+    from chromevol_enhanced_b200 import accounting
+    mu = max(0.0, -Q.diagonal().min())
+    Qs = Q + mu * np.eye(Q.shape[0])
+    nu = min(np.abs(Qs).sum(axis=0).max(), np.abs(Qs).sum(axis=1).max())
+    kind, nc, s = accounting.plan_pairs(times, [nu], [mu])
+    return kind[0], nc[0], s[0], nu, mu
 
 
 @pytest.mark.parametrize("N", [35, 100])
@@ -68,22 +78,21 @@ def test_fused_p_columns_match_oracle(N):
     rows = synthetic.random_param_rows(12, seed=4, linear='positive')
     rows[::3, 8] = 7
     times = np.concatenate([[0.0, 1e-6], 1e-4 + np.random.default_rng(1).exponential(0.05, 5), [0.758285]])
-    w, mode, norm1 = _apply(rows, times, N)
+    w, mode, norms = _apply(rows, times, N)
     n_fused = 0
     for b in range(rows.shape[0]):
         Q = O.build_q(synthetic.row_to_dict(rows[b]), N)
-        assert norm1[b] == pytest.approx(np.abs(Q).sum(axis=0).max(), rel=1e-14)
+        kind, nc, sq, nu, mu = _host_plan(Q, times)
+        assert norms[b, 0] == pytest.approx(np.abs(Q).sum(axis=0).max(), rel=1e-14)
+        assert norms[b, 11] == pytest.approx(mu, rel=1e-14)
+        assert norms[b, 12] == pytest.approx(nu, rel=1e-13)
         for e, t in enumerate(times):
-            eta = t * norm1[b]
-            if t == 0.0:
-                assert (mode[b, e] == 1).all()          # identity, AR:146-148
-            elif eta > 5.4:
-                assert (mode[b, e] == 2).all()          # routed to the scaling-and-squaring kernel
-            else:
-                assert (mode[b, e] == 0).all()
+            # 1: identity (t == 0, AR:146-148); 2: routed to the scaling-and-squaring kernel
+            assert (mode[b, e] == kind[e]).all(), (b, t, kind[e])
+            if kind[e] == 0:
                 P = w[b, e].T                           # w[k] = column k of P
                 ref = O.transition_probabilities(Q, t)
-                assert np.abs(P - ref).max() <= 1e-12, (b, t, eta)
+                assert np.abs(P - ref).max() <= 1e-12, (b, t, nu * t)
                 n_fused += 1
     assert n_fused > 40
 
@@ -96,29 +105,32 @@ def test_fused_general_variant_on_one_hot_children():
     times = np.array([0.002, 0.03, 0.09])
     N = 100
     eye = np.eye(N + 1)
-    w, mode, norm1 = _apply(rows, times, N, child_vectors=eye, codes=np.full(N + 1, -2))
+    w, mode, norms = _apply(rows, times, N, child_vectors=eye, codes=np.full(N + 1, -2))
     for b in range(rows.shape[0]):
         Q = O.build_q(synthetic.row_to_dict(rows[b]), N)
         for e, t in enumerate(times):
-            if t * norm1[b] > 5.4:
+            if mode[b, e, 0] != 0:
                 continue
             assert np.abs(w[b, e].T - O.transition_probabilities(Q, t)).max() <= 1e-12
 
 
-def test_fused_p_eta_sweep_up_to_theta():
-    """Series length selection: eta = t ||Q||_1 swept from 1e-6 to the 5.4 switch-over."""
+def test_fused_p_sweep_up_to_the_switch_over():
+    """Series length selection: x = nu t swept from 1e-6 up to where 40 terms stop sufficing."""
     from chromevol_enhanced_b200 import synthetic
     row = synthetic.default_param_row()
     row[:5] = [2.0, 1.5, 0.7, 0.4, 0.3]
     Q = O.build_q(synthetic.row_to_dict(row), 100)
-    norm1 = np.abs(Q).sum(axis=0).max()
-    etas = np.array([1e-6, 1e-3, 0.05, 0.3, 0.9, 1.7, 2.5, 3.3, 4.1, 4.9, 5.39])
-    times = etas / norm1
+    _, _, _, nu, mu = _host_plan(Q, np.array([1.0]))
+    xs = np.array([1e-6, 1e-3, 0.05, 0.3, 0.9, 1.7, 2.5, 3.3, 4.1, 4.9, 5.7, 6.5, 6.9, 7.5, 9.0])
+    times = xs / nu
+    kind, nc, sq, _, _ = _host_plan(Q, times)
+    assert kind[0] == 0 and kind[-1] == 2 and nc[:len(nc) - 2].max() >= 38
     w, mode, _ = _apply(row, times, 100)
     for e, t in enumerate(times):
-        assert (mode[0, e] == 0).all()
-        ref = O.transition_probabilities(Q, t)
-        assert np.abs(w[0, e].T - ref).max() <= 1e-12, etas[e]
+        assert (mode[0, e] == kind[e]).all()
+        if kind[e] == 0:
+            ref = O.transition_probabilities(Q, t)
+            assert np.abs(w[0, e].T - ref).max() <= 1e-12, xs[e]
 
 
 def test_fused_non_generator_q():
@@ -127,7 +139,7 @@ def test_fused_non_generator_q():
     from chromevol_enhanced_b200 import synthetic
     rows = synthetic.random_param_rows(10, seed=9, linear='mixed')
     times = np.array([0.003, 0.02, 0.05])
-    w, mode, norm1 = _apply(rows, times, 100)
+    w, mode, norms = _apply(rows, times, 100)
     checked = 0
     for b in range(rows.shape[0]):
         Q = O.build_q(synthetic.row_to_dict(rows[b]), 100)
@@ -154,11 +166,11 @@ def test_fused_child_vector_kinds_and_ragged_groups():
     K = 11
     vecs = rng.random((K, N + 1)) * 10.0 ** rng.integers(-30, 1, size=(K, 1))
     codes = np.array([-2, -2, -1, 5, -2, 100, -2, -1, 0, -2, 37], dtype=np.int32)
-    w, mode, norm1 = _apply(rows, times, N, child_vectors=vecs, codes=codes)
+    w, mode, norms = _apply(rows, times, N, child_vectors=vecs, codes=codes)
     for b in range(rows.shape[0]):
         Q = O.build_q(synthetic.row_to_dict(rows[b]), N)
         for e, t in enumerate(times):
-            if t * norm1[b] > 5.4:
+            if mode[b, e, 0] != 0:
                 continue
             P = O.transition_probabilities(Q, t)
             for k in range(K):
@@ -175,7 +187,7 @@ def test_fused_odd_sizes(N):
     rows = np.stack([synthetic.default_param_row(), synthetic.default_param_row(base_number=3)])
     rows[1, :5] = [0.8, 0.6, 0.3, 0.1, 0.05]
     times = np.array([0.004, 0.11, 0.6])
-    w, mode, norm1 = _apply(rows, times, N)
+    w, mode, norms = _apply(rows, times, N)
     for b in range(2):
         Q = O.build_q(synthetic.row_to_dict(rows[b]), N)
         for e, t in enumerate(times):
@@ -186,7 +198,7 @@ def test_fused_odd_sizes(N):
 
 
 def _series_matrices(rows, times, N):
-    """post(expm(Q_b t_e)) for the pairs with t ||Q||_1 > 5.4 through cevb_expm_plan +
+    """post(expm(Q_b t_e)) for the pairs that need squarings through cevb_expm_plan +
     cevb_taylor_matrices; returns (P[slot], slot[b, e], squarings[slot], nan_count)."""
     import torch
     from chromevol_enhanced_b200 import _lib
@@ -222,7 +234,7 @@ def _series_matrices(rows, times, N):
 
 @pytest.mark.parametrize("N", [35, 100, 111])
 def test_series_squaring_matrices_match_oracle(N):
-    """Pairs beyond the 5.4 switch-over: series at t 2^-s, s squarings, post-processing."""
+    """Pairs beyond the switch-over: series at t 2^-s, s squarings, post-processing."""
     from chromevol_enhanced_b200 import synthetic
     rows = synthetic.random_param_rows(8, seed=4, linear='positive')
     rows[:, :5] *= 4.0
@@ -233,14 +245,14 @@ def test_series_squaring_matrices_match_oracle(N):
     n_checked = 0
     for b in range(rows.shape[0]):
         Q = O.build_q(synthetic.row_to_dict(rows[b]), N)
-        norm1 = np.abs(Q).sum(axis=0).max()
+        kind, nc, s_host, nu, mu = _host_plan(Q, times)
         for e, t in enumerate(times):
-            if t * norm1 > 5.4:
+            if kind[e] == 2:
                 k = slot[b, e]
                 assert k >= 0
-                assert sq[k] == int(np.ceil(np.log2(t * norm1 / 5.4)))
+                assert sq[k] == s_host[e] and sq[k] >= 1
                 ref = O.transition_probabilities(Q, t)
-                assert np.abs(P[k] - ref).max() <= 1e-12, (b, t, t * norm1, sq[k])
+                assert np.abs(P[k] - ref).max() <= 1e-12, (b, t, nu * t, sq[k])
                 n_checked += 1
             else:
                 assert slot[b, e] == -1
