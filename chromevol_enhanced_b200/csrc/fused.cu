@@ -97,7 +97,6 @@ __global__ void __launch_bounds__(128) q_structure_kernel(const double* __restri
                                                           uint16_t* __restrict__ csc,
                                                           uint8_t* __restrict__ csc_cnt) {
     __shared__ double red[4];
-    __shared__ double s_mu;
     const int b = blockIdx.x, tid = threadIdx.x;
     const double* Q = pw + (size_t)b * CEVB_NPOW * n * ldq;
     uint16_t* idx_c = csc + (size_t)b * 2 * CEVB_MAX_SPARSE * n;
@@ -157,7 +156,6 @@ __global__ void __launch_bounds__(128) q_structure_kernel(const double* __restri
         out[CEVB_NORM_SHIFT] = anynan ? NAN : mu;
         out[CEVB_NORM_SHIFTED] = anynan ? NAN : fmin(nu1, nui);
     }
-    (void)s_mu;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -405,7 +403,6 @@ __global__ void __launch_bounds__(32 * (NW + 1)) taylor_apply_kernel(ApplyArgs a
 
     const int nj = npad >> 3;
     const int npass = (nj + F_JT - 1) / F_JT;
-    const int nitems = (i_end - i_begin) * npass;
     const int stage_doubles = ck * F_JT * 32;
     int ns = a.stage_doubles_cap / stage_doubles;
     if (ns > F_MAXSTAGE) ns = F_MAXSTAGE;
@@ -479,6 +476,16 @@ __global__ void __launch_bounds__(32 * (NW + 1)) taylor_apply_kernel(ApplyArgs a
             }
         }
     }
+    // fast path: tile index holding the wanted even / odd column (-1: not in this lane)
+    int sel0[G], sel1[G];
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) {
+        sel0[gi] = (my_jt[gi] >= 0 && my_half[gi] == 0) ? my_jt[gi] : -1;
+        sel1[gi] = (my_jt[gi] >= 0 && my_half[gi] == 1) ? my_jt[gi] : -1;
+    }
+    const bool fast = (npad == F_JT * 8);
+    const double fl_last0 = ((F_JT - 1) * 8 + 2 * t4 < n) ? 1e-12 : 0.0;
+    const double fl_last1 = ((F_JT - 1) * 8 + 2 * t4 + 1 < n) ? 1e-12 : 0.0;
     double rs0[G], rs1[G], dt0[G], dt1[G];
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) rs0[gi] = rs1[gi] = dt0[gi] = dt1[gi] = 0.0;
@@ -540,29 +547,57 @@ __global__ void __launch_bounds__(32 * (NW + 1)) taylor_apply_kernel(ApplyArgs a
                 continue;
             }
             // floor, row sum and dot product with L_child on the accumulator fragments
+            if (fast) {
+                // one pass of exactly 13 tiles (97 <= n <= 104): branch-free.  The padding
+                // columns of the last tile hold exact zeros (zero coefficients), so giving them
+                // a "floor" of 0 removes them from the row sum.
 #pragma unroll
-            for (int gi = 0; gi < G; ++gi) {
-                const double* Lrow = Ls + (size_t)((warp * G + gi) * 8 + g) * ldl + j0 + 2 * t4;
-                const int sel_jt = my_jt[gi] - pass * F_JT;
+                for (int gi = 0; gi < G; ++gi) {
+                    const double* Lrow = Ls + (size_t)((warp * G + gi) * 8 + g) * ldl + 2 * t4;
 #pragma unroll
-                for (int jt = 0; jt < F_JT; ++jt) {
-                    if (njt == F_JT || jt < njt) {
+                    for (int jt = 0; jt < F_JT; ++jt) {
                         double p0 = acc[gi][jt][0], p1 = acc[gi][jt][1];
-                        if (__double_as_longlong(p0) < floor_bits) p0 = 1e-12;  // AR:153
-                        if (__double_as_longlong(p1) < floor_bits) p1 = 1e-12;
-                        if (has_pad && jt == njt - 1) {  // the tile holding the padding columns
-                            const int j = j0 + jt * 8 + 2 * t4;
-                            if (j >= n) p0 = 0.0;
-                            if (j + 1 >= n) p1 = 0.0;
-                        }
+                        const double f0 = (jt == F_JT - 1) ? fl_last0 : 1e-12;
+                        const double f1 = (jt == F_JT - 1) ? fl_last1 : 1e-12;
+                        p0 = (__double_as_longlong(p0) < floor_bits) ? f0 : p0;  // AR:153
+                        p1 = (__double_as_longlong(p1) < floor_bits) ? f1 : p1;
                         rs0[gi] += p0;
                         rs1[gi] += p1;
                         if (MODE == APPLY_LEAF) {
-                            if (jt == sel_jt) dt0[gi] = my_half[gi] ? p1 : p0;
+                            dt0[gi] = (jt == sel0[gi]) ? p0 : dt0[gi];
+                            dt0[gi] = (jt == sel1[gi]) ? p1 : dt0[gi];
                         } else {
                             const double2 l = *reinterpret_cast<const double2*>(Lrow + jt * 8);
                             dt0[gi] = fma(p0, l.x, dt0[gi]);
                             dt1[gi] = fma(p1, l.y, dt1[gi]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int gi = 0; gi < G; ++gi) {
+                    const double* Lrow = Ls + (size_t)((warp * G + gi) * 8 + g) * ldl + j0 + 2 * t4;
+                    const int sel_jt = my_jt[gi] - pass * F_JT;
+#pragma unroll
+                    for (int jt = 0; jt < F_JT; ++jt) {
+                        if (jt < njt) {
+                            double p0 = acc[gi][jt][0], p1 = acc[gi][jt][1];
+                            if (__double_as_longlong(p0) < floor_bits) p0 = 1e-12;  // AR:153
+                            if (__double_as_longlong(p1) < floor_bits) p1 = 1e-12;
+                            if (has_pad && jt == njt - 1) {  // the tile holding the padding columns
+                                const int j = j0 + jt * 8 + 2 * t4;
+                                if (j >= n) p0 = 0.0;
+                                if (j + 1 >= n) p1 = 0.0;
+                            }
+                            rs0[gi] += p0;
+                            rs1[gi] += p1;
+                            if (MODE == APPLY_LEAF) {
+                                if (jt == sel_jt) dt0[gi] = my_half[gi] ? p1 : p0;
+                            } else {
+                                const double2 l = *reinterpret_cast<const double2*>(Lrow + jt * 8);
+                                dt0[gi] = fma(p0, l.x, dt0[gi]);
+                                dt1[gi] = fma(p1, l.y, dt1[gi]);
+                            }
                         }
                     }
                 }
@@ -740,7 +775,7 @@ static int launch_apply_variant(ApplyArgs& a, int B, cudaStream_t st) {
     const size_t one_stage = sizeof(double) * (size_t)F_KC * F_JT * 32;
     if (fixed + one_stage > g_f_optin) return 1;  // does not fit: caller tries a smaller variant
     size_t ring = g_f_optin - fixed;
-    const size_t ring_max = (NW >= 16 ? F_MAXSTAGE : 2) * one_stage;  // narrow CTAs: leave room for 2-3 per SM
+    size_t ring_max = (NW >= 16 ? F_MAXSTAGE : 1) * one_stage;  // narrow CTAs: more of them per SM
     if (ring > ring_max) ring = ring_max;
     a.stage_doubles_cap = (int)(ring / sizeof(double));
     const size_t smem = fixed + ring;
@@ -764,11 +799,16 @@ static int launch_apply_variant(ApplyArgs& a, int B, cudaStream_t st) {
 
 template <int MODE>
 static int launch_apply_shapes(ApplyArgs& a, int B, cudaStream_t st) {
-    // CTA shapes from widest to narrowest; small launches use fewer warps so that more CTAs fit
+    // CTA shapes.  The kernel is latency-bound per warp (every warp alternates a DMMA phase and
+    // an epilogue phase), so many narrow CTAs per SM beat few wide ones except for the long
+    // all-leaves list, where wide CTAs share each coefficient tile among 128 branches.
+    // (thresholds measured on B200 with tools/level_probe.py; CEVB_T16 / CEVB_T4 override them)
     int rc = 1;
-    if (a.n_items > 64) rc = launch_apply_variant<1, 16, MODE>(a, B, st);
-    if (rc == 1 && a.n_items > 32) rc = launch_apply_variant<1, 8, MODE>(a, B, st);
-    if (rc == 1 && a.n_items > 16) rc = launch_apply_variant<1, 4, MODE>(a, B, st);
+    const int t16 = getenv("CEVB_T16") ? atoi(getenv("CEVB_T16")) : 300;
+    const int t4 = getenv("CEVB_T4") ? atoi(getenv("CEVB_T4")) : 16;
+    if (a.n_items > t16) rc = launch_apply_variant<1, 16, MODE>(a, B, st);
+    if (rc == 1 && a.n_items > t4) rc = launch_apply_variant<1, 4, MODE>(a, B, st);
+    if (rc == 1 && a.n_items > t4) rc = launch_apply_variant<1, 8, MODE>(a, B, st);  // large n
     if (rc == 1) rc = launch_apply_variant<1, 2, MODE>(a, B, st);
     return rc;
 }

@@ -69,14 +69,14 @@ class ExpmWorkspace:
         else:
             self.P = torch.empty((max(self.p_slots, 1), n, self.ldp), **f64)
         self.info = torch.zeros((cap, n_t), dtype=torch.int32, device=device)
-        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.counter = torch.zeros(16, dtype=torch.int32, device=device)
         if n_nodes:
             self.tc = torch.empty((cap, lib.cevb_taylor_doubles(n)), **f64)
             self.slot = torch.empty((cap, n_t), dtype=torch.int32, device=device)
             self.worklist = torch.empty(max(self.p_slots, 1), dtype=torch.int32, device=device)
             self.work_s = torch.zeros(max(self.p_slots, 1), dtype=torch.int32, device=device)
-            self.nan_count = torch.zeros(1, dtype=torch.int32, device=device)
-            self.work_count = torch.zeros(1, dtype=torch.int32, device=device)
+            self.nan_count = torch.zeros(16, dtype=torch.int32, device=device)
+            self.work_count = torch.zeros(16, dtype=torch.int32, device=device)   # one per stream
             self.w = torch.zeros((cap, n_nodes, self.ldp), **f64)
             self.wr = torch.ones((cap, n_nodes, self.ldp), **f64)
             self.mode = torch.zeros((cap, n_nodes), dtype=torch.uint8, device=device)
@@ -95,7 +95,7 @@ class LikelihoodEngine:
     """Tree + data resident on the device; evaluates batches of parameter vectors."""
 
     def __init__(self, flat: FlatTree, device=None, max_workspace_bytes=32 << 30, chunk=None,
-                 path="fused", squaring="series"):
+                 path="fused", squaring="series", n_streams=4):
         """path: "fused" (series on the tensor cores, P never written for t||Q||_1 <= 5.4) or
         "materialised" (every P by the Pade kernel).  squaring: how the fused path forms the
         matrices that need scaling and squaring -- "series" (series at t 2^-s + squarings in
@@ -106,6 +106,8 @@ class LikelihoodEngine:
         if squaring not in ("series", "pade"):
             raise ValueError("squaring must be 'series' or 'pade'")
         self.path = path
+        self.n_streams = max(1, min(16, int(n_streams)))
+        self._streams = None
         if squaring == "series" and not _lib.load().cevb_taylor_matrices_supported(flat.n_states):
             squaring = "pade"     # two n x n matrices do not fit in shared memory
         self.squaring = squaring
@@ -165,7 +167,8 @@ class LikelihoodEngine:
         self._ws = None
         self._node_vec = None
         if self.path == "fused":
-            slots = int(min(cap * self.flat.n_t, max(self.p_budget // self.mat_bytes, self.flat.n_t)))
+            slots = int(min(max(cap, self.n_streams) * self.flat.n_t,
+                            max(self.p_budget // self.mat_bytes, self.n_streams * self.flat.n_t)))
             self._ws = ExpmWorkspace(self.n, self.flat.n_t, cap, self.device, p_slots=slots,
                                      n_nodes=self.flat.n_nodes)
         else:
@@ -220,53 +223,52 @@ class LikelihoodEngine:
             _lib.ptr(self._logl), _lib.ptr(self._rescales), _stream_ptr()), "cevb_prune")
         self._mark("prune", e0)
 
-    def _fused_chunk(self, ws, nb, d_root_freq, full_pivot=0):
-        lib, st, f = self.lib, _stream_ptr(), self.flat
+    def _fused_slice(self, ws, lo, hi, k, d_root_freq, full_pivot, st):
+        """Vectors [lo, hi) of the chunk, work-list partition k, all launches on stream `st`."""
+        lib, f, nb = self.lib, self.flat, hi - lo
+        P = lambda t: _lib.ptr(t[lo:])                       # per-vector buffers
+        pps = ws.p_slots // self.n_streams                   # P slots of one partition
+        Q = lambda t: _lib.ptr(t[k * pps:])                  # per-partition work-list buffers
+        one = lambda t: _lib.ptr(t[k:])
         e0 = self._mark("prepare")
-        _lib.check(lib.cevb_build_q(_lib.ptr(ws.params), nb, self.n, _lib.ptr(ws.pw), st),
-                   "cevb_build_q")
-        _lib.check(lib.cevb_taylor_prepare(_lib.ptr(ws.pw), nb, self.n, _lib.ptr(ws.norms),
-                                           _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt), _lib.ptr(ws.tc),
-                                           st), "cevb_taylor_prepare")
-        _lib.check(lib.cevb_expm_plan(_lib.ptr(ws.norms), _lib.ptr(self.d_t), nb, f.n_t,
-                                      ws.p_slots, _lib.ptr(ws.slot), _lib.ptr(ws.worklist),
-                                      _lib.ptr(ws.work_s), _lib.ptr(ws.work_count), st),
+        _lib.check(lib.cevb_build_q(P(ws.params), nb, self.n, P(ws.pw), st), "cevb_build_q")
+        _lib.check(lib.cevb_taylor_prepare(P(ws.pw), nb, self.n, P(ws.norms), P(ws.csc),
+                                           P(ws.csc_cnt), P(ws.tc), st), "cevb_taylor_prepare")
+        _lib.check(lib.cevb_expm_plan(P(ws.norms), _lib.ptr(self.d_t), nb, f.n_t, pps, P(ws.slot),
+                                      Q(ws.worklist), Q(ws.work_s), one(ws.work_count), st),
                    "cevb_expm_plan")
         e1 = self._mark("prepare", e0)
         if self.squaring == "series":
             _lib.check(lib.cevb_taylor_matrices(
-                _lib.ptr(ws.tc), _lib.ptr(ws.norms), _lib.ptr(self.d_t), _lib.ptr(self.d_t_order),
-                nb, f.n_t, self.n, _lib.ptr(ws.slot), _lib.ptr(ws.work_s), _lib.ptr(ws.work_count),
-                ws.p_slots, _lib.ptr(ws.P), _lib.ptr(ws.counter), _lib.ptr(ws.nan_count), st),
-                "cevb_taylor_matrices")
+                P(ws.tc), P(ws.norms), _lib.ptr(self.d_t), _lib.ptr(self.d_t_order), nb, f.n_t,
+                self.n, P(ws.slot), Q(ws.work_s), one(ws.work_count), pps, Q(ws.P),
+                one(ws.counter), one(ws.nan_count), st), "cevb_taylor_matrices")
         else:
             # Pade-13 + scaling and squaring (the scipy algorithm) for the listed pairs
-            _lib.check(lib.cevb_expm_prepare(_lib.ptr(ws.pw), nb, self.n, _lib.ptr(ws.norms),
-                                             _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt), st),
-                       "cevb_expm_prepare")
+            _lib.check(lib.cevb_expm_prepare(P(ws.pw), nb, self.n, P(ws.norms), P(ws.csc),
+                                             P(ws.csc_cnt), st), "cevb_expm_prepare")
             _lib.check(lib.cevb_expm_branches_list(
-                _lib.ptr(ws.pw), _lib.ptr(ws.norms), _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt),
-                _lib.ptr(self.d_t), nb, f.n_t, self.n, _lib.ptr(ws.P), _lib.ptr(ws.info),
-                _lib.ptr(ws.scratch), _lib.ptr(ws.counter), full_pivot, _lib.ptr(ws.worklist),
-                _lib.ptr(ws.work_count), ws.p_slots, st), "cevb_expm_branches_list")
+                P(ws.pw), P(ws.norms), P(ws.csc), P(ws.csc_cnt), _lib.ptr(self.d_t), nb, f.n_t,
+                self.n, Q(ws.P), P(ws.info), _lib.ptr(ws.scratch), one(ws.counter), full_pivot,
+                Q(ws.worklist), one(ws.work_count), pps, st), "cevb_expm_branches_list")
         e2 = self._mark("expm", e1)
 
-        def prune(lo, hi, stages):
+        def prune(l0, l1, stages):
             _lib.check(lib.cevb_prune_fused(
-                _lib.ptr(ws.tc), _lib.ptr(ws.norms), _lib.ptr(ws.P), _lib.ptr(ws.slot), nb, f.n_t,
-                self.n, f.n_nodes, f.root, _lib.ptr(self.d_level_nodes),
+                P(ws.tc), P(ws.norms), Q(ws.P), P(ws.slot), nb, f.n_t, self.n, f.n_nodes, f.root,
+                _lib.ptr(self.d_level_nodes),
                 self.h_level_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), f.n_levels,
                 _lib.ptr(self.d_child_off), _lib.ptr(self.d_child_idx), _lib.ptr(self.d_branch_of),
                 _lib.ptr(self.d_leaf_code), _lib.ptr(self.d_level_child),
                 self.h_level_child_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
-                _lib.ptr(self.d_leaf_child), int(f.leaf_child.size), _lib.ptr(self.d_t_node), _lib.ptr(d_root_freq), _lib.ptr(self._node_vec),
-                _lib.ptr(ws.w), _lib.ptr(ws.wr), _lib.ptr(ws.mode), _lib.ptr(self._logl), _lib.ptr(self._rescales),
-                lo, hi, stages, st), "cevb_prune_fused")
+                _lib.ptr(self.d_leaf_child), int(f.leaf_child.size), _lib.ptr(self.d_t_node),
+                _lib.ptr(d_root_freq), P(self._node_vec), P(ws.w), P(ws.wr), P(ws.mode),
+                P(self._logl), P(self._rescales), l0, l1, stages, st), "cevb_prune_fused")
 
         if self.stage_events is None:
             prune(0, f.n_levels, FUSED_ALL)
         else:
-            # same launches, issued level by level so the two kernels can be timed separately
+            # same launches, issued level by level so the kernels can be timed separately
             prune(0, 0, FUSED_INIT)
             ev = self._mark("init", e2)
             prune(0, 0, FUSED_LEAVES)
@@ -277,20 +279,51 @@ class LikelihoodEngine:
                 prune(lv, lv + 1, FUSED_COMBINE)
                 ev = self._mark("combine", ev)
 
+    def _fused_chunk(self, ws, nb, d_root_freq, full_pivot=0):
+        """One chunk: its vectors are split over `n_streams` CUDA streams so that the narrow
+        upper tree levels of one slice (latency-bound: few branches per coefficient tile)
+        overlap the wide lower levels of another.  Stage timing runs on the caller's stream."""
+        S = self.n_streams if (self.stage_events is None and nb >= 2 * self.n_streams
+                               and self.squaring == "series") else 1   # the Pade scratch is shared
+        cur = torch.cuda.current_stream()
+        if S == 1:
+            self._fused_slice(ws, 0, nb, 0, d_root_freq, full_pivot,
+                              ctypes.c_void_p(cur.cuda_stream))
+            return
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams)]
+        start = torch.cuda.Event()
+        start.record(cur)
+        per = (nb + S - 1) // S
+        for k in range(S):
+            lo, hi = k * per, min(nb, (k + 1) * per)
+            if hi <= lo:
+                continue
+            stream = self._streams[k]
+            stream.wait_event(start)
+            self._fused_slice(ws, lo, hi, k, d_root_freq, full_pivot,
+                              ctypes.c_void_p(stream.cuda_stream))
+            done = torch.cuda.Event()
+            done.record(stream)
+            cur.wait_event(done)
+
     def _run_chunk(self, d_params_chunk, d_root_freq, full_pivot=0):
         nb = d_params_chunk.shape[0]
         ws = self._ws
         ws.params[:nb].copy_(d_params_chunk)
         if self.path == "fused":
+            ws.work_count.zero_()
             self._fused_chunk(ws, nb, d_root_freq, full_pivot)
+            pps = ws.p_slots // self.n_streams
             if self.squaring == "pade":
                 self._growth_flag |= ((ws.info[:nb] >> 16) & INFO_GROWTH).any()
-            self._overflow_flag |= (ws.work_count[0] > ws.p_slots)
-            self._materialised += ws.work_count[0].to(torch.int64)
+            self._overflow_flag |= (ws.work_count > pps).any()
+            self._materialised += ws.work_count.sum().to(torch.int64)
             if self.keep_info:
-                cnt = int(min(int(ws.work_count[0]), ws.p_slots))
-                self.info_log.append((ws.work_s[:cnt].cpu().numpy().copy(),
-                                      ws.slot[:nb].cpu().numpy().copy(),
+                cnts = torch.clamp(ws.work_count, max=pps).cpu().numpy()
+                s_list = np.concatenate([ws.work_s[k * pps:k * pps + int(c)].cpu().numpy()
+                                         for k, c in enumerate(cnts)])
+                self.info_log.append((s_list, ws.slot[:nb].cpu().numpy().copy(),
                                       ws.norms[:nb].cpu().numpy().copy()))
             return
         self._transition_matrices(ws, nb, full_pivot)
@@ -347,7 +380,7 @@ class LikelihoodEngine:
                 # more pairs needed a materialised matrix than P has slots: redo the batch in
                 # chunks small enough that every pair of a chunk fits
                 self.overflow_events += 1
-                step = max(1, self._ws.p_slots // max(self.flat.n_t, 1))
+                step = max(1, (self._ws.p_slots // self.n_streams) // max(self.flat.n_t, 1))
                 continue
             if flags[0] and not full_pivot:
                 # a tripped element-growth monitor (not seen in practice) redoes the batch with
