@@ -188,6 +188,7 @@ def run_ours(args):
     tree, counts, rows = build_workload(args.batch, rank)
     flat = FlatTree(tree, counts, MAX_CHR)
     eng = LikelihoodEngine(flat, device=dev, max_workspace_bytes=args.workspace_gb << 30)
+    eng.want_node_vectors = False      # logL only; switched on for the single-vector + states case
     B = rows.shape[0]
     d_rows = torch.as_tensor(rows, device=dev)
     h_rows = torch.as_tensor(rows).pin_memory()
@@ -264,6 +265,7 @@ def run_ours(args):
 
     # ---- single-vector latency, BASELINE configs[1] (logL + ancestral states)
     one = d_rows[:1].clone()
+    eng.want_node_vectors = True
     from chromevol_enhanced_b200 import synthetic
     one.copy_(torch.as_tensor(synthetic.default_param_row()[None], device=dev))
     for _ in range(3):

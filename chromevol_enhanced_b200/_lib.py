@@ -64,6 +64,7 @@ _PROTOTYPES = {
                                            c_dp, c_dp, _c.c_void_p]),
     "cevb_diag_fp64_peak": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, c_dp, _c.c_void_p]),
     "cevb_diag_set_phase_buffer": (_c.c_int, [c_dp]),
+    "cevb_diag_dmma_probe": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _c.c_int, c_dp, _c.c_void_p]),
 }
 
 # symbols include/chromevol_b200.h declares (the CPU test-suite checks every one is exported)

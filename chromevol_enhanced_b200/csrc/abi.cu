@@ -50,6 +50,103 @@ __global__ void __launch_bounds__(512) dfma_peak_kernel(int iters, double* out) 
     if (s == 123.456) out[0] = s;
 }
 
+// Diagnostic: DMMA throughput as a function of resident warps, with 13 independent accumulator
+// tiles per warp (the apply kernel's shape); smem != 0 loads every B fragment from shared
+// memory right before its DMMA (one LDS.64 per DMMA), smem == 2 double-buffers them in registers.
+__global__ void __launch_bounds__(512) dmma_probe_kernel(int iters, int smem_mode, double* out) {
+    __shared__ double sb[13 * 32 * 8];
+    for (int x = threadIdx.x; x < 13 * 32 * 8; x += blockDim.x) sb[x] = 1.0 + 1e-9 * x;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    double c[13][2];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) c[i][0] = c[i][1] = 0.0;
+    const double av = 1.0 + threadIdx.x * 1e-9;
+    double bv = 1.0 - threadIdx.x * 1e-9;
+    if (smem_mode == 0) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 13; ++i) dmma884(c[i][0], c[i][1], av, bv);
+        }
+    } else if (smem_mode == 1) {
+        for (int it = 0; it < iters; ++it) {
+            const double* bp = sb + (it & 7) * 13 * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < 13; ++i) dmma884(c[i][0], c[i][1], av, bp[i * 32]);
+        }
+    } else if (smem_mode == 5) {
+        // 13 volatile loads (kept in program order by ptxas) and then the 13 DMMAs
+        for (int it = 0; it < iters; ++it) {
+            const volatile double* bp = sb + (it & 7) * 13 * 32 + lane;
+            double bc[13];
+#pragma unroll
+            for (int i = 0; i < 13; ++i) bc[i] = bp[i * 32];
+#pragma unroll
+            for (int i = 0; i < 13; ++i) dmma884(c[i][0], c[i][1], av, bc[i]);
+        }
+    } else if (smem_mode == 6) {
+        // two register sets: the volatile loads of iteration it+1 are issued before the DMMAs of it
+        double b0[13], b1[13];
+        {
+            const volatile double* bp = sb + lane;
+#pragma unroll
+            for (int i = 0; i < 13; ++i) b0[i] = bp[i * 32];
+        }
+        for (int it = 0; it < iters; it += 2) {
+            const volatile double* bp1 = sb + ((it + 1) & 7) * 13 * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < 13; ++i) b1[i] = bp1[i * 32];
+#pragma unroll
+            for (int i = 0; i < 13; ++i) dmma884(c[i][0], c[i][1], av, b0[i]);
+            const volatile double* bp0 = sb + ((it + 2) & 7) * 13 * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < 13; ++i) b0[i] = bp0[i * 32];
+#pragma unroll
+            for (int i = 0; i < 13; ++i) dmma884(c[i][0], c[i][1], av, b1[i]);
+        }
+    } else if (smem_mode == 4) {
+        // six LDS.128 (two tiles each) + one LDS.64 per 13 DMMAs
+        for (int it = 0; it < iters; ++it) {
+            const double* bp = sb + (it & 7) * 13 * 32;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const double2 b2 = *reinterpret_cast<const double2*>(bp + (i * 32 + lane) * 2);
+                dmma884(c[2 * i][0], c[2 * i][1], av, b2.x);
+                dmma884(c[2 * i + 1][0], c[2 * i + 1][1], av, b2.y);
+            }
+            dmma884(c[12][0], c[12][1], av, bp[12 * 32 + lane]);
+        }
+    } else if (smem_mode == 3) {
+        for (int it = 0; it < iters; ++it) {
+            const double* bp = sb + (it & 7) * 13 * 32 + lane;
+            double bc[13];
+#pragma unroll
+            for (int i = 0; i < 13; ++i) bc[i] = bp[i * 32];
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 13; ++i) dmma884(c[i][0], c[i][1], av, bc[i]);
+            asm volatile("" ::: "memory");
+        }
+    } else {
+        double bc[13];
+#pragma unroll
+        for (int i = 0; i < 13; ++i) bc[i] = sb[i * 32 + lane];
+        for (int it = 0; it < iters; ++it) {
+            const double* bp = sb + ((it + 1) & 7) * 13 * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < 13; ++i) {
+                const double b0 = bc[i];
+                bc[i] = bp[i * 32];
+                dmma884(c[i][0], c[i][1], av, b0);
+            }
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s + bv;
+}
+
 }  // namespace cevb
 
 using namespace cevb;
@@ -82,6 +179,13 @@ extern "C" int cevb_device_info(int* sm_count, int* cc_major, int* cc_minor, siz
 
 // Diagnostics (not part of the reference-facing surface): launches `blocks` CTAs of 512 threads
 // that each issue iters*8 DMMA.8x8x4 per warp (kind 0) or iters*16 DFMA per thread (kind 1).
+extern "C" int cevb_diag_dmma_probe(int blocks, int threads, int iters, int smem_mode, double* out,
+                                    void* stream) {
+    dmma_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, smem_mode, out);
+    CEVB_CHECK_LAUNCH("dmma probe");
+    return 0;
+}
+
 extern "C" int cevb_diag_fp64_peak(int kind, int blocks, int iters, double* out, void* stream) {
     if (kind == 0)
         dmma_peak_kernel<<<blocks, 512, 0, (cudaStream_t)stream>>>(iters, out);

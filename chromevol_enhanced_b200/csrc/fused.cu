@@ -23,6 +23,9 @@
 // Branches with eta > 5.4 need squarings and therefore a materialised matrix: they are routed
 // (cevb_expm_plan) to the Pade kernel of expm.cu, whose P the combine kernel reads.
 #include <stdlib.h>
+#ifndef CEVB_EXP
+#define CEVB_EXP 0
+#endif
 
 #include "common.cuh"
 
@@ -178,13 +181,48 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
     const uint8_t* cnt_c = csc_cnt + (size_t)b * 2 * n;
     double* out = tc + ((size_t)b * n + i) * F_KC * npad * 4;
     const double mu = norms[(size_t)b * CEVB_NNORM + CEVB_NORM_SHIFT];
+    // The sparse column of (Q + mu I) this thread multiplies with is the same for all 39
+    // steps: keep it in registers (<= 12 entries + the shift), so a step is shared-memory loads
+    // and FMAs only.  Threads own column tid (and tid + 128, ... for n > 128, handled by the
+    // generic path below with the structure re-read from global memory).
+    const int j0 = tid;
+    int cnt0 = 0;
+    int ridx[CEVB_MAX_SPARSE];
+    double qval[CEVB_MAX_SPARSE];
+#pragma unroll
+    for (int q = 0; q < CEVB_MAX_SPARSE; ++q) {
+        ridx[q] = 0;
+        qval[q] = 0.0;
+    }
+    if (j0 < n) {
+        cnt0 = cnt_c[j0];
+        if (cnt0 != 255) {
+#pragma unroll
+            for (int q = 0; q < CEVB_MAX_SPARSE; ++q) {
+                if (q < cnt0) {
+                    ridx[q] = idx_c[(size_t)q * n + j0];
+                    qval[q] = Q[(size_t)ridx[q] * ldq + j0];
+                }
+            }
+        }
+    }
     for (int j = tid; j < npad; j += 128) cur[j] = (j == i) ? 1.0 : 0.0;
     __syncthreads();
     for (int k = 0; k < 4 * F_KC; ++k) {
         for (int j = tid; j < npad; j += 128) stg[j * 4 + (k & 3)] = (j < n) ? cur[j] : 0.0;
         if (k + 1 < 4 * F_KC) {
-            const double inv_den = (double)(k + 1);
-            for (int j = tid; j < n; j += 128) {
+            const double den = (double)(k + 1);
+            if (j0 < n) {
+                double acc = cur[j0] * mu;
+                if (cnt0 == 255) {
+                    for (int r = 0; r < n; ++r) acc = fma(cur[r], Q[(size_t)r * ldq + j0], acc);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < CEVB_MAX_SPARSE; ++q) acc = fma(cur[ridx[q]], qval[q], acc);
+                }
+                nxt[j0] = acc / den;
+            }
+            for (int j = tid + 128; j < n; j += 128) {   // n > 128
                 const int cnt = cnt_c[j];
                 double acc = cur[j] * mu;
                 if (cnt == 255) {
@@ -195,7 +233,7 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
                         acc = fma(cur[r], Q[(size_t)r * ldq + j], acc);
                     }
                 }
-                nxt[j] = acc / inv_den;
+                nxt[j] = acc / den;
             }
         }
         __syncthreads();
@@ -319,8 +357,9 @@ __host__ __device__ inline size_t apply_fixed_bytes(int eb, int ldl) {  // ldl =
 // is a select of one accumulator and no child vectors are staged.  MODE APPLY_EVAL: no
 // epilogue arithmetic at all -- the series value at the scaled time t 2^-s of every pair with
 // t ||Q||_1 > theta is written out for the squaring kernel.
-template <int G, int NW, int MODE>
-__global__ void __launch_bounds__(32 * (NW + 1)) taylor_apply_kernel(ApplyArgs a) {
+template <int G, int NW, int MODE, bool FAST>
+__global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4))
+    taylor_apply_kernel(ApplyArgs a) {
     constexpr bool LEAF = MODE != APPLY_GENERAL;   // no child vectors in shared memory
     constexpr bool EVAL = MODE == APPLY_EVAL;
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -438,6 +477,9 @@ __global__ void __launch_bounds__(32 * (NW + 1)) taylor_apply_kernel(ApplyArgs a
         int s = 0, use = 0;
         for (int i = i_begin; i < i_end; ++i) {
             for (int pass = 0; pass < npass; ++pass) {
+#if CEVB_EXP == 4 || CEVB_EXP == 5 || CEVB_EXP == 9
+                if (use > 0) return;
+#endif
                 if (use > 0) {
                     const uint32_t par = (uint32_t)((use - 1) & 1);
                     while (!mbar_try_wait(&empty[s], par)) __nanosleep(64);
@@ -460,166 +502,176 @@ __global__ void __launch_bounds__(32 * (NW + 1)) taylor_apply_kernel(ApplyArgs a
     }
     if (wk == 0) return;  // consumer warp without fused branches (not counted in `empty`)
 
-    // ---- consumers
+    // ---- consumers (one group of 8 branches per warp)
+    static_assert(G == 1, "the pipelined consumer loop keeps one group per warp");
     const long long floor_bits = __double_as_longlong(1e-12);
-    // LEAF: the lane / tile / half that holds column `code` of each of the warp's groups
-    int my_jt[G], my_half[G];
-#pragma unroll
-    for (int gi = 0; gi < G; ++gi) {
-        my_jt[gi] = -1;
-        my_half[gi] = 0;
-        if (MODE == APPLY_LEAF) {
-            const int code = s_code[(warp * G + gi) * 8 + g];
-            if (code >= 0 && ((code >> 1) & 3) == t4) {
-                my_jt[gi] = code >> 3;   // tile index along the whole row (pass * F_JT + jt)
-                my_half[gi] = code & 1;
-            }
+    const int xw = warp * 8 + g;                       // this lane's branch within the CTA
+    // LEAF: the tile / half of the row that holds column `code` of this lane's branch
+    int my_jt = -1, my_half = 0;
+    if (MODE == APPLY_LEAF) {
+        const int code = s_code[xw];
+        if (code >= 0 && ((code >> 1) & 3) == t4) {
+            my_jt = code >> 3;   // tile index along the whole row (pass * F_JT + jt)
+            my_half = code & 1;
         }
     }
-    // fast path: tile index holding the wanted even / odd column (-1: not in this lane)
-    int sel0[G], sel1[G];
-#pragma unroll
-    for (int gi = 0; gi < G; ++gi) {
-        sel0[gi] = (my_jt[gi] >= 0 && my_half[gi] == 0) ? my_jt[gi] : -1;
-        sel1[gi] = (my_jt[gi] >= 0 && my_half[gi] == 1) ? my_jt[gi] : -1;
-    }
-    const bool fast = (npad == F_JT * 8);
+    const int sel0 = (my_jt >= 0 && my_half == 0) ? my_jt : -1;   // fast path (one pass)
+    const int sel1 = (my_jt >= 0 && my_half == 1) ? my_jt : -1;
+    constexpr bool fast = FAST;   // exactly one pass of 13 tiles (97 <= n <= 104), host-checked
     const double fl_last0 = ((F_JT - 1) * 8 + 2 * t4 < n) ? 1e-12 : 0.0;
     const double fl_last1 = ((F_JT - 1) * 8 + 2 * t4 + 1 < n) ? 1e-12 : 0.0;
-    double rs0[G], rs1[G], dt0[G], dt1[G];
-#pragma unroll
-    for (int gi = 0; gi < G; ++gi) rs0[gi] = rs1[gi] = dt0[gi] = dt1[gi] = 0.0;
-    const double* Aw = As + (size_t)(warp * G) * F_KC * 32 + lane;
     const bool has_pad = npad != n;
+    const bool mine = s_nc[xw] > 0;
+    const int my_child = s_child[xw];
+    const double* Aw = As + (size_t)warp * F_KC * 32 + lane;
+    const double* Lbase = Ls + (size_t)xw * ldl + 2 * t4;
+    double rs0 = 0.0, rs1 = 0.0, dt0 = 0.0, dt1 = 0.0;
+    double acc[F_JT][2];
+
+    // epilogue of one accumulator tile of the item (row i_e, pass pass_e): floor (AR:153), row
+    // sum, dot product with L_child -- or the raw store for the squaring kernel
+    auto epi_tile = [&](const int jt, double p0, double p1, const int i_e, const int pass_e,
+                        const int njt_e) {
+        if (EVAL) {
+            const int j = pass_e * F_JT * 8 + jt * 8 + 2 * t4;
+            if (mine && jt < njt_e && j < a.ldp)
+                *reinterpret_cast<double2*>(a.X + ((size_t)my_child * n + i_e) * a.ldp + j) =
+                    make_double2(p0, p1);
+            return;
+        }
+        if (fast) {
+            // one pass of exactly 13 tiles (97 <= n <= 104): branch-free.  The padding columns
+            // of the last tile hold exact zeros (zero coefficients), so a "floor" of 0 removes
+            // them from the row sum.
+            const double f0 = (jt == F_JT - 1) ? fl_last0 : 1e-12;
+            const double f1 = (jt == F_JT - 1) ? fl_last1 : 1e-12;
+            p0 = (__double_as_longlong(p0) < floor_bits) ? f0 : p0;
+            p1 = (__double_as_longlong(p1) < floor_bits) ? f1 : p1;
+            rs0 += p0;
+            rs1 += p1;
+            if (MODE == APPLY_LEAF) {
+                dt0 = (jt == sel0) ? p0 : dt0;
+                dt0 = (jt == sel1) ? p1 : dt0;
+            } else {
+                const double2 l = *reinterpret_cast<const double2*>(Lbase + jt * 8);
+                dt0 = fma(p0, l.x, dt0);
+                dt1 = fma(p1, l.y, dt1);
+            }
+        } else if (jt < njt_e) {
+            const int j0 = pass_e * F_JT * 8;
+            if (__double_as_longlong(p0) < floor_bits) p0 = 1e-12;
+            if (__double_as_longlong(p1) < floor_bits) p1 = 1e-12;
+            if (has_pad && jt == njt_e - 1) {  // the tile that may hold padding columns
+                const int j = j0 + jt * 8 + 2 * t4;
+                if (j >= n) p0 = 0.0;
+                if (j + 1 >= n) p1 = 0.0;
+            }
+            rs0 += p0;
+            rs1 += p1;
+            if (MODE == APPLY_LEAF) {
+                if (jt == my_jt - pass_e * F_JT) dt0 = my_half ? p1 : p0;
+            } else {
+                const double2 l = *reinterpret_cast<const double2*>(Lbase + j0 + jt * 8);
+                dt0 = fma(p0, l.x, dt0);
+                dt1 = fma(p1, l.y, dt1);
+            }
+        }
+    };
+    // end of a row: quad reduction and the two stores (the combine kernel forms d / r, AR:154)
+    auto finish_row = [&](const int i_e) {
+        if (EVAL) return;
+#if CEVB_EXP == 8 || CEVB_EXP == 9
+        if (rs0 == 1.2345e-300) a.w[i_e] = dt0;
+        return;
+#endif
+        double r = rs0 + rs1, d = dt0 + dt1;
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        r += __shfl_xor_sync(0xffffffffu, r, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        if (t4 == 0 && mine) {
+            const size_t o = ((size_t)b * a.n_nodes + my_child) * a.ldp + i_e;
+            a.w[o] = d;
+            a.wr[o] = r;
+        }
+        rs0 = rs1 = dt0 = dt1 = 0.0;
+    };
+
+    // Software pipeline over the items (row, pass): while the first chunk of item q is issued
+    // to the tensor pipe, the finished accumulator tiles of item q-1 are read out one by one
+    // and post-processed, so a warp keeps the FP64 pipe fed during its own epilogue.
     int s = 0;
     uint32_t par = 0;
+    int i_prev = 0, pass_prev = 0, njt_prev = 0;
+    bool have_prev = false;
+
     for (int i = i_begin; i < i_end; ++i) {
         for (int pass = 0; pass < npass; ++pass) {
-            const int j0 = pass * F_JT * 8;
             const int njt = min(F_JT, nj - pass * F_JT);
-            double acc[G][F_JT][2];
-#pragma unroll
-            for (int gi = 0; gi < G; ++gi)
-#pragma unroll
-                for (int jt = 0; jt < F_JT; ++jt) {
-                    acc[gi][jt][0] = 0.0;
-                    acc[gi][jt][1] = 0.0;
-                }
+#if CEVB_EXP != 4 && CEVB_EXP != 5 && CEVB_EXP != 9
             mbar_wait(&full[s], par);
+#endif
             const double* Bq = Bs + (size_t)s * stage_doubles + lane;
-            for (int c = 0; c < wk; ++c) {
-                double av[G];
+            // Per chunk: the 13 B-fragment loads are issued back to back into 13 registers and
+            // only then the 13 DMMAs (the compiler barriers keep ptxas from re-interleaving
+            // them: an LDS placed right before its DMMA, or right after a DMMA that still has to
+            // read the same register, serialises the warp on the shared-memory latency -- see
+            // tools/dmma_probe.py).  Tiles beyond njt (last pass of a wide row) multiply stale
+            // shared memory; their accumulators are never read.
+            double bv[F_JT];
+            {
+                const double av = Aw[0];
 #pragma unroll
-                for (int gi = 0; gi < G; ++gi) av[gi] = Aw[(size_t)(gi * F_KC + c) * 32];
-                const double* Bc = Bq + (size_t)c * F_JT * 32;
-                // tiles beyond njt (last pass of a wide row) multiply stale shared memory; their
-                // accumulators are never read
+                for (int jt = 0; jt < F_JT; ++jt) bv[jt] = Bq[jt * 32];
+                asm volatile("" ::: "memory");
 #pragma unroll
                 for (int jt = 0; jt < F_JT; ++jt) {
-                    const double bv = Bc[jt * 32];
-#pragma unroll
-                    for (int gi = 0; gi < G; ++gi)
-                        dmma884(acc[gi][jt][0], acc[gi][jt][1], av[gi], bv);
+                    const double p0 = acc[jt][0], p1 = acc[jt][1];
+                    acc[jt][0] = 0.0;
+                    acc[jt][1] = 0.0;
+                    dmma884(acc[jt][0], acc[jt][1], av, bv[jt]);
+#if CEVB_EXP < 3 || CEVB_EXP == 8
+                    if (have_prev) epi_tile(jt, p0, p1, i_prev, pass_prev, njt_prev);
+#else
+#if CEVB_EXP == 5 || CEVB_EXP == 6 || CEVB_EXP == 9
+                    if ((__double2hiint(p0) ^ __double2hiint(p1)) == 0x12345678) rs0 += 1.0;
+#else
+                    if (p0 == 1.2345e-300 || p1 == 1.2345e-300) rs0 += 1.0;
+#endif
+#endif
                 }
+                asm volatile("" ::: "memory");
+            }
+            for (int c = 1; c < wk; ++c) {
+                const double av = Aw[(size_t)c * 32];
+                const double* Bc = Bq + (size_t)c * F_JT * 32;
+#pragma unroll
+                for (int jt = 0; jt < F_JT; ++jt) bv[jt] = Bc[jt * 32];
+                asm volatile("" ::: "memory");
+#pragma unroll
+                for (int jt = 0; jt < F_JT; ++jt) dmma884(acc[jt][0], acc[jt][1], av, bv[jt]);
+                asm volatile("" ::: "memory");
             }
             // every shared-memory read of this stage has been consumed by an issued DMMA
             __syncwarp();
+#if CEVB_EXP != 4 && CEVB_EXP != 5 && CEVB_EXP != 9
             if (lane == 0) mbar_arrive(&empty[s]);
+#endif
             if (++s == ns) {
                 s = 0;
                 par ^= 1u;
             }
-
-            if (EVAL) {
-#pragma unroll
-                for (int gi = 0; gi < G; ++gi) {
-                    const int x = (warp * G + gi) * 8 + g;
-                    if (s_nc[x] > 0) {
-                        double* xrow = a.X + ((size_t)s_child[x] * n + i) * a.ldp + j0 + 2 * t4;
-#pragma unroll
-                        for (int jt = 0; jt < F_JT; ++jt) {
-                            if (jt < njt && j0 + jt * 8 + 2 * t4 < a.ldp)
-                                *reinterpret_cast<double2*>(xrow + jt * 8) =
-                                    make_double2(acc[gi][jt][0], acc[gi][jt][1]);
-                        }
-                    }
-                }
-                continue;
-            }
-            // floor, row sum and dot product with L_child on the accumulator fragments
-            if (fast) {
-                // one pass of exactly 13 tiles (97 <= n <= 104): branch-free.  The padding
-                // columns of the last tile hold exact zeros (zero coefficients), so giving them
-                // a "floor" of 0 removes them from the row sum.
-#pragma unroll
-                for (int gi = 0; gi < G; ++gi) {
-                    const double* Lrow = Ls + (size_t)((warp * G + gi) * 8 + g) * ldl + 2 * t4;
-#pragma unroll
-                    for (int jt = 0; jt < F_JT; ++jt) {
-                        double p0 = acc[gi][jt][0], p1 = acc[gi][jt][1];
-                        const double f0 = (jt == F_JT - 1) ? fl_last0 : 1e-12;
-                        const double f1 = (jt == F_JT - 1) ? fl_last1 : 1e-12;
-                        p0 = (__double_as_longlong(p0) < floor_bits) ? f0 : p0;  // AR:153
-                        p1 = (__double_as_longlong(p1) < floor_bits) ? f1 : p1;
-                        rs0[gi] += p0;
-                        rs1[gi] += p1;
-                        if (MODE == APPLY_LEAF) {
-                            dt0[gi] = (jt == sel0[gi]) ? p0 : dt0[gi];
-                            dt0[gi] = (jt == sel1[gi]) ? p1 : dt0[gi];
-                        } else {
-                            const double2 l = *reinterpret_cast<const double2*>(Lrow + jt * 8);
-                            dt0[gi] = fma(p0, l.x, dt0[gi]);
-                            dt1[gi] = fma(p1, l.y, dt1[gi]);
-                        }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int gi = 0; gi < G; ++gi) {
-                    const double* Lrow = Ls + (size_t)((warp * G + gi) * 8 + g) * ldl + j0 + 2 * t4;
-                    const int sel_jt = my_jt[gi] - pass * F_JT;
-#pragma unroll
-                    for (int jt = 0; jt < F_JT; ++jt) {
-                        if (jt < njt) {
-                            double p0 = acc[gi][jt][0], p1 = acc[gi][jt][1];
-                            if (__double_as_longlong(p0) < floor_bits) p0 = 1e-12;  // AR:153
-                            if (__double_as_longlong(p1) < floor_bits) p1 = 1e-12;
-                            if (has_pad && jt == njt - 1) {  // the tile holding the padding columns
-                                const int j = j0 + jt * 8 + 2 * t4;
-                                if (j >= n) p0 = 0.0;
-                                if (j + 1 >= n) p1 = 0.0;
-                            }
-                            rs0[gi] += p0;
-                            rs1[gi] += p1;
-                            if (MODE == APPLY_LEAF) {
-                                if (jt == sel_jt) dt0[gi] = my_half[gi] ? p1 : p0;
-                            } else {
-                                const double2 l = *reinterpret_cast<const double2*>(Lrow + jt * 8);
-                                dt0[gi] = fma(p0, l.x, dt0[gi]);
-                                dt1[gi] = fma(p1, l.y, dt1[gi]);
-                            }
-                        }
-                    }
-                }
-            }
-            if (pass == npass - 1) {
-#pragma unroll
-                for (int gi = 0; gi < G; ++gi) {
-                    double r = rs0[gi] + rs1[gi], d = dt0[gi] + dt1[gi];
-                    r += __shfl_xor_sync(0xffffffffu, r, 1);
-                    d += __shfl_xor_sync(0xffffffffu, d, 1);
-                    r += __shfl_xor_sync(0xffffffffu, r, 2);
-                    d += __shfl_xor_sync(0xffffffffu, d, 2);
-                    const int x = (warp * G + gi) * 8 + g;
-                    if (t4 == 0 && s_nc[x] > 0) {
-                        const size_t o = ((size_t)b * a.n_nodes + s_child[x]) * a.ldp + i;
-                        a.w[o] = d;    // the combine kernel forms d / r (AR:154, AR:237)
-                        a.wr[o] = r;
-                    }
-                    rs0[gi] = rs1[gi] = dt0[gi] = dt1[gi] = 0.0;
-                }
-            }
+            if (have_prev && pass_prev == npass - 1) finish_row(i_prev);
+            have_prev = true;
+            i_prev = i;
+            pass_prev = pass;
+            njt_prev = njt;
         }
+    }
+    if (have_prev) {
+#pragma unroll
+        for (int jt = 0; jt < F_JT; ++jt) epi_tile(jt, acc[jt][0], acc[jt][1], i_prev, pass_prev, njt_prev);
+        finish_row(i_prev);
     }
 }
 
@@ -699,21 +751,30 @@ __global__ void __launch_bounds__(CT) combine_level_kernel(
             } else {
                 for (int j = tid; j < n; j += CT) Lc[j] = (code == -1) ? unif : cv[j];
                 __syncthreads();
-                for (int i = warp * 2; i < n; i += 2 * (CT / 32)) {
+                // four rows per warp in flight: this path is a single CTA streaming 80 KB, so it
+                // is bound by how many loads it keeps outstanding
+                for (int i = warp * 4; i < n; i += 4 * (CT / 32)) {
                     const double* r0 = Pm + (size_t)i * ldp;
-                    const bool two = (i + 1) < n;
-                    const double* r1 = two ? r0 + ldp : r0;
-                    double a0 = 0.0, a1 = 0.0;
+                    const double* r1 = (i + 1 < n) ? r0 + ldp : r0;
+                    const double* r2 = (i + 2 < n) ? r0 + 2 * ldp : r0;
+                    const double* r3 = (i + 3 < n) ? r0 + 3 * ldp : r0;
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
                     for (int j = lane; j < n; j += 32) {
                         const double l = Lc[j];
                         a0 = fma(r0[j], l, a0);
                         a1 = fma(r1[j], l, a1);
+                        a2 = fma(r2[j], l, a2);
+                        a3 = fma(r3[j], l, a3);
                     }
                     a0 = warp_sum(a0);
                     a1 = warp_sum(a1);
+                    a2 = warp_sum(a2);
+                    a3 = warp_sum(a3);
                     if (lane == 0) {
                         v[i] *= a0;
-                        if (two) v[i + 1] *= a1;
+                        if (i + 1 < n) v[i + 1] *= a1;
+                        if (i + 2 < n) v[i + 2] *= a2;
+                        if (i + 3 < n) v[i + 3] *= a3;
                     }
                 }
             }
@@ -768,14 +829,23 @@ static int fused_query() {
     return 0;
 }
 
+template <int G, int NW, int MODE, bool FAST>
+static int launch_apply_fast(ApplyArgs& a, int B, cudaStream_t st);
+
 template <int G, int NW, int MODE>
 static int launch_apply_variant(ApplyArgs& a, int B, cudaStream_t st) {
+    if (MODE != APPLY_EVAL && a.npad == F_JT * 8) return launch_apply_fast<G, NW, MODE, true>(a, B, st);
+    return launch_apply_fast<G, NW, MODE, false>(a, B, st);
+}
+
+template <int G, int NW, int MODE, bool FAST>
+static int launch_apply_fast(ApplyArgs& a, int B, cudaStream_t st) {
     constexpr int EB = NW * G * 8;
     const size_t fixed = apply_fixed_bytes(EB, MODE != APPLY_GENERAL ? 0 : a.ldl);
     const size_t one_stage = sizeof(double) * (size_t)F_KC * F_JT * 32;
     if (fixed + one_stage > g_f_optin) return 1;  // does not fit: caller tries a smaller variant
     size_t ring = g_f_optin - fixed;
-    size_t ring_max = (NW >= 16 ? F_MAXSTAGE : 1) * one_stage;  // narrow CTAs: more of them per SM
+    size_t ring_max = (NW >= 15 ? F_MAXSTAGE : (NW == 7 ? 2 : 1)) * one_stage;  // narrow CTAs: more per SM
     if (ring > ring_max) ring = ring_max;
     a.stage_doubles_cap = (int)(ring / sizeof(double));
     const size_t smem = fixed + ring;
@@ -790,9 +860,9 @@ static int launch_apply_variant(ApplyArgs& a, int B, cudaStream_t st) {
     a.rows_per_cta = (a.n + ry - 1) / ry;
     ry = (a.n + a.rows_per_cta - 1) / a.rows_per_cta;
     dim3 grid(gx, ry, B);
-    CEVB_CHECK_CUDA(cudaFuncSetAttribute(taylor_apply_kernel<G, NW, MODE>,
+    CEVB_CHECK_CUDA(cudaFuncSetAttribute(taylor_apply_kernel<G, NW, MODE, FAST>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    taylor_apply_kernel<G, NW, MODE><<<grid, 32 * (NW + 1), smem, st>>>(a);
+    taylor_apply_kernel<G, NW, MODE, FAST><<<grid, 32 * (NW + 1), smem, st>>>(a);
     CEVB_CHECK_LAUNCH("taylor_apply_kernel");
     return 0;
 }
@@ -802,14 +872,16 @@ static int launch_apply_shapes(ApplyArgs& a, int B, cudaStream_t st) {
     // CTA shapes.  The kernel is latency-bound per warp (every warp alternates a DMMA phase and
     // an epilogue phase), so many narrow CTAs per SM beat few wide ones except for the long
     // all-leaves list, where wide CTAs share each coefficient tile among 128 branches.
-    // (thresholds measured on B200 with tools/level_probe.py; CEVB_T16 / CEVB_T4 override them)
+    // (thresholds measured on B200 with tools/level_probe.py; CEVB_TW / CEVB_TM / CEVB_TS override them)
     int rc = 1;
-    const int t16 = getenv("CEVB_T16") ? atoi(getenv("CEVB_T16")) : 300;
-    const int t4 = getenv("CEVB_T4") ? atoi(getenv("CEVB_T4")) : 16;
-    if (a.n_items > t16) rc = launch_apply_variant<1, 16, MODE>(a, B, st);
-    if (rc == 1 && a.n_items > t4) rc = launch_apply_variant<1, 4, MODE>(a, B, st);
-    if (rc == 1 && a.n_items > t4) rc = launch_apply_variant<1, 8, MODE>(a, B, st);  // large n
-    if (rc == 1) rc = launch_apply_variant<1, 2, MODE>(a, B, st);
+    const int tw = getenv("CEVB_TW") ? atoi(getenv("CEVB_TW")) : 300;    // wide: 15 consumer warps
+    const int tm = getenv("CEVB_TM") ? atoi(getenv("CEVB_TM")) : 100000; // medium: 7
+    const int ts = getenv("CEVB_TS") ? atoi(getenv("CEVB_TS")) : 8;      // small: 3, else 1
+    if (a.n_items > tw) rc = launch_apply_variant<1, 15, MODE>(a, B, st);
+    if (rc == 1 && a.n_items > tm) rc = launch_apply_variant<1, 7, MODE>(a, B, st);
+    if (rc == 1 && a.n_items > ts) rc = launch_apply_variant<1, 3, MODE>(a, B, st);
+    if (rc == 1 && a.n_items > ts) rc = launch_apply_variant<1, 7, MODE>(a, B, st);  // large n
+    if (rc == 1) rc = launch_apply_variant<1, 1, MODE>(a, B, st);
     return rc;
 }
 
@@ -1067,6 +1139,10 @@ extern "C" int cevb_prune_fused(const double* tc, const double* norms, const dou
     if (stages & CEVB_FUSED_INIT) {
         CEVB_CHECK_CUDA(cudaMemsetAsync(rescales, 0, sizeof(int32_t) * (size_t)B, st));
         CEVB_CHECK_CUDA(cudaMemsetAsync(mode, 0, (size_t)B * n_nodes, st));
+    }
+    if (stages & CEVB_FUSED_LEAFVEC) {
+        // conditional-likelihood vectors of the leaves: outputs only (the kernels build the
+        // one-hot / uniform child vectors from leaf_code), so callers that want only logL skip it
         dim3 lgrid(n_nodes, B);
         leaf_init_fused_kernel<<<lgrid, 128, 0, st>>>(n, ldp, n_nodes, leaf_code, node_vec);
         CEVB_CHECK_LAUNCH("leaf_init_kernel");

@@ -25,7 +25,7 @@ from .flatten import FlatTree
 PARAM_ORDER = ['gain', 'loss', 'dupl', 'demidupl_gain', 'demidupl_loss',
                'base_number_gain', 'base_number_loss', 'linear_rate', 'base_number']
 
-FUSED_INIT, FUSED_APPLY, FUSED_COMBINE, FUSED_LEAVES, FUSED_ALL = 1, 2, 4, 8, 15
+FUSED_INIT, FUSED_APPLY, FUSED_COMBINE, FUSED_LEAVES, FUSED_LEAFVEC, FUSED_ALL = 1, 2, 4, 8, 16, 31
 INFO_IDENTITY_T0 = 1
 INFO_NAN_FALLBACK = 2
 INFO_GROWTH = 4
@@ -149,6 +149,9 @@ class LikelihoodEngine:
                 chunk = max(1, min(4096, int(max_workspace_bytes // max(per_vec, 1))))
             self.p_budget = None
         self.mat_bytes = mat_bytes
+        # leaf rows of node_vec are outputs only; batched logL callers (bench, optimiser) switch
+        # them off, the drop-in classes read node vectors and keep them on
+        self.want_node_vectors = True
         self.chunk = int(chunk)
         self.overflow_events = 0
         self._ws = None
@@ -265,11 +268,12 @@ class LikelihoodEngine:
                 _lib.ptr(d_root_freq), P(self._node_vec), P(ws.w), P(ws.wr), P(ws.mode),
                 P(self._logl), P(self._rescales), l0, l1, stages, st), "cevb_prune_fused")
 
+        leafvec = FUSED_LEAFVEC if self.want_node_vectors else 0
         if self.stage_events is None:
-            prune(0, f.n_levels, FUSED_ALL)
+            prune(0, f.n_levels, FUSED_ALL & ~FUSED_LEAFVEC | leafvec)
         else:
             # same launches, issued level by level so the kernels can be timed separately
-            prune(0, 0, FUSED_INIT)
+            prune(0, 0, FUSED_INIT | leafvec)
             ev = self._mark("init", e2)
             prune(0, 0, FUSED_LEAVES)
             ev = self._mark("apply", ev)
@@ -344,7 +348,8 @@ class LikelihoodEngine:
             return 9 + levels
         applies = int(self.flat.leaf_child.size > 0) + \
             int(np.count_nonzero(np.diff(self.flat.level_child_off)))
-        return (7 if self.squaring == "series" else 12) + levels + applies
+        base = (6 if self.squaring == "series" else 11) + (1 if self.want_node_vectors else 0)
+        return base + levels + applies
 
     # ------------------------------------------------------------------ public
     def log_likelihood(self, params, root_freq=None, check_growth=True):

@@ -50,7 +50,8 @@ extern "C" {
 #define CEVB_FUSED_APPLY 2
 #define CEVB_FUSED_COMBINE 4
 #define CEVB_FUSED_LEAVES 8
-#define CEVB_FUSED_ALL 15
+#define CEVB_FUSED_LEAFVEC 16   /* also write node_vec of the leaves (AR:201-214); output only */
+#define CEVB_FUSED_ALL 31
 
 /* norms[b][.] */
 #define CEVB_NORM_ONE 0      /* ||Q||_1 */
@@ -170,7 +171,8 @@ int cevb_taylor_apply(const double* tc, const double* norms, int B, int n, int n
  *                             cevb_expm_branches_list (E = row length of slot),
  *   w, wr [B][n_nodes][ldp], mode [B][n_nodes]   scratch.
  * Levels [level_begin, level_end) are processed; `stages` is a mask of CEVB_FUSED_INIT (zero
- * mode / rescales, write the leaf vectors), CEVB_FUSED_LEAVES (the leaf_child launch),
+ * mode / rescales), CEVB_FUSED_LEAFVEC (write the leaf rows of node_vec; needed only when the
+ * caller reads node_vec, not for logL), CEVB_FUSED_LEAVES (the leaf_child launch),
  * CEVB_FUSED_APPLY and CEVB_FUSED_COMBINE.  The whole tree in one call is (0, n_levels,
  * CEVB_FUSED_ALL); the split form lets a caller time the kernels separately. */
 int cevb_prune_fused(const double* tc, const double* norms, const double* P, const int32_t* slot,
