@@ -38,7 +38,7 @@ _PROTOTYPES = {
                                            _c.c_longlong, _c.c_void_p]),
     "cevb_taylor_doubles": (_c.c_size_t, [_c.c_int]),
     "cevb_taylor_matrices_supported": (_c.c_int, [_c.c_int]),
-    "cevb_taylor_prepare": (_c.c_int, [c_dp, _c.c_int, _c.c_int, c_dp, c_dp, c_dp, c_dp,
+    "cevb_taylor_prepare": (_c.c_int, [c_dp, _c.c_int, _c.c_int, _c.c_double, c_dp, c_dp, c_dp, c_dp,
                                        _c.c_void_p]),
     "cevb_expm_plan": (_c.c_int, [c_dp, c_dp, _c.c_int, _c.c_int, _c.c_longlong, c_dp, c_dp, c_dp,
                                   c_dp, _c.c_void_p]),

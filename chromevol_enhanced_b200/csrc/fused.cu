@@ -165,26 +165,35 @@ __global__ void __launch_bounds__(128) q_structure_kernel(const double* __restri
 // C_0 = I, C_k = C_{k-1} (Q + mu I) / k, one CTA per (row i, vector b); row i of C_k only needs
 // row i of C_{k-1}.  Output layout tc[b][i][c][j][4]: chunk c holds degrees 4c..4c+3 interleaved per
 // column, exactly the B-operand fragment order of DMMA (lane 4g+t <- column g, degree t).
+constexpr int TCR = 4;   // rows of C_k per CTA of the coefficient kernel
+
 __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restrict__ pw,
                                                            const uint16_t* __restrict__ csc,
                                                            const uint8_t* __restrict__ csc_cnt,
                                                            const double* __restrict__ norms,
-                                                           int n, int ldq, int npad,
+                                                           int n, int ldq, int npad, double t_max,
                                                            double* __restrict__ tc) {
     extern __shared__ double shc[];
-    double* cur = shc;
-    double* nxt = shc + npad;
-    double* stg = shc + 2 * npad;  // [npad][4]
-    const int i = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    double* cur = shc;                    // [TCR][npad]
+    double* nxt = shc + TCR * npad;       // [TCR][npad]
+    double* stg = shc + 2 * TCR * npad;   // [TCR][npad][4]
+    const int i0 = blockIdx.x * TCR, b = blockIdx.y, tid = threadIdx.x;
     const double* Q = pw + (size_t)b * CEVB_NPOW * n * ldq;
     const uint16_t* idx_c = csc + (size_t)b * 2 * CEVB_MAX_SPARSE * n;
     const uint8_t* cnt_c = csc_cnt + (size_t)b * 2 * n;
-    double* out = tc + ((size_t)b * n + i) * F_KC * npad * 4;
     const double mu = norms[(size_t)b * CEVB_NNORM + CEVB_NORM_SHIFT];
-    // The sparse column of (Q + mu I) this thread multiplies with is the same for all 39
-    // steps: keep it in registers (<= 12 entries + the shift), so a step is shared-memory loads
-    // and FMAs only.  Threads own column tid (and tid + 128, ... for n > 128, handled by the
-    // generic path below with the structure re-read from global memory).
+    // chunks any branch of this vector can need: the longest branch decides (all of them when
+    // it has to be scaled and squared, or when the caller gives no bound)
+    int kc_need = F_KC;
+    if (t_max > 0.0) {
+        const PairPlan pp = plan_pair(t_max, norms[(size_t)b * CEVB_NNORM + CEVB_NORM_SHIFTED], mu);
+        if (pp.kind == 0) kc_need = (pp.nc + 3) >> 2;
+    }
+    const int k_end = 4 * kc_need;
+    // The sparse column of (Q + mu I) a thread multiplies with is the same for every row and
+    // all 39 steps: it is kept in registers (<= 12 entries), so a step is shared-memory loads
+    // and FMAs only, for TCR rows at once.  Columns beyond 128 (n > 128) and columns with more
+    // than 12 non-zeros re-read the structure from global memory.
     const int j0 = tid;
     int cnt0 = 0;
     int ridx[CEVB_MAX_SPARSE];
@@ -206,40 +215,62 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
             }
         }
     }
-    for (int j = tid; j < npad; j += 128) cur[j] = (j == i) ? 1.0 : 0.0;
+    for (int x = tid; x < TCR * npad; x += 128) {
+        const int r = x / npad, j = x - r * npad;
+        cur[x] = (j == i0 + r) ? 1.0 : 0.0;
+    }
     __syncthreads();
-    for (int k = 0; k < 4 * F_KC; ++k) {
-        for (int j = tid; j < npad; j += 128) stg[j * 4 + (k & 3)] = (j < n) ? cur[j] : 0.0;
-        if (k + 1 < 4 * F_KC) {
-            const double den = (double)(k + 1);
+    for (int k = 0; k < k_end; ++k) {
+        for (int x = tid; x < TCR * npad; x += 128) {
+            const int r = x / npad, j = x - r * npad;
+            stg[(size_t)(r * npad + j) * 4 + (k & 3)] = (j < n) ? cur[x] : 0.0;
+        }
+        if (k + 1 < k_end) {
+            const double inv = 1.0 / (double)(k + 1);
             if (j0 < n) {
-                double acc = cur[j0] * mu;
+                double acc[TCR];
+#pragma unroll
+                for (int r = 0; r < TCR; ++r) acc[r] = cur[r * npad + j0] * mu;
                 if (cnt0 == 255) {
-                    for (int r = 0; r < n; ++r) acc = fma(cur[r], Q[(size_t)r * ldq + j0], acc);
+                    for (int rr = 0; rr < n; ++rr) {
+                        const double q = Q[(size_t)rr * ldq + j0];
+#pragma unroll
+                        for (int r = 0; r < TCR; ++r) acc[r] = fma(cur[r * npad + rr], q, acc[r]);
+                    }
                 } else {
 #pragma unroll
-                    for (int q = 0; q < CEVB_MAX_SPARSE; ++q) acc = fma(cur[ridx[q]], qval[q], acc);
+                    for (int q = 0; q < CEVB_MAX_SPARSE; ++q) {
+#pragma unroll
+                        for (int r = 0; r < TCR; ++r) acc[r] = fma(cur[r * npad + ridx[q]], qval[q], acc[r]);
+                    }
                 }
-                nxt[j0] = acc / den;
+#pragma unroll
+                for (int r = 0; r < TCR; ++r) nxt[r * npad + j0] = acc[r] * inv;
             }
             for (int j = tid + 128; j < n; j += 128) {   // n > 128
                 const int cnt = cnt_c[j];
-                double acc = cur[j] * mu;
-                if (cnt == 255) {
-                    for (int r = 0; r < n; ++r) acc = fma(cur[r], Q[(size_t)r * ldq + j], acc);
-                } else {
-                    for (int q = 0; q < cnt; ++q) {
-                        const int r = idx_c[(size_t)q * n + j];
-                        acc = fma(cur[r], Q[(size_t)r * ldq + j], acc);
-                    }
+                double acc[TCR];
+#pragma unroll
+                for (int r = 0; r < TCR; ++r) acc[r] = cur[r * npad + j] * mu;
+                const int lim = (cnt == 255) ? n : cnt;
+                for (int q = 0; q < lim; ++q) {
+                    const int rr = (cnt == 255) ? q : idx_c[(size_t)q * n + j];
+                    const double qv = Q[(size_t)rr * ldq + j];
+#pragma unroll
+                    for (int r = 0; r < TCR; ++r) acc[r] = fma(cur[r * npad + rr], qv, acc[r]);
                 }
-                nxt[j] = acc / den;
+#pragma unroll
+                for (int r = 0; r < TCR; ++r) nxt[r * npad + j] = acc[r] * inv;
             }
         }
         __syncthreads();
         if ((k & 3) == 3) {
-            double* dst = out + (size_t)(k >> 2) * npad * 4;
-            for (int x = tid; x < npad * 4; x += 128) dst[x] = stg[x];
+            for (int r = 0; r < TCR; ++r) {
+                if (i0 + r >= n) break;
+                double* dst = tc + (((size_t)b * n + i0 + r) * F_KC + (k >> 2)) * npad * 4;
+                const double* src = stg + (size_t)r * npad * 4;
+                for (int x = tid; x < npad * 4; x += 128) dst[x] = src[x];
+            }
             __syncthreads();
         }
         double* sw = cur;
@@ -1026,8 +1057,8 @@ extern "C" size_t cevb_taylor_doubles(int n) {
     return (size_t)n * F_KC * round_up(n, 8) * 4;
 }
 
-extern "C" int cevb_taylor_prepare(const double* pw, int B, int n, double* norms, uint16_t* csc,
-                                   uint8_t* csc_cnt, double* tc, void* stream) {
+extern "C" int cevb_taylor_prepare(const double* pw, int B, int n, double t_max, double* norms,
+                                   uint16_t* csc, uint8_t* csc_cnt, double* tc, void* stream) {
     if (B <= 0) return 0;
     if (B > 65535) {
         set_error("cevb_taylor_prepare: B=%d exceeds one launch; chunk the batch", B);
@@ -1037,9 +1068,12 @@ extern "C" int cevb_taylor_prepare(const double* pw, int B, int n, double* norms
     const int npad = round_up(n, 8);
     q_structure_kernel<<<B, 128, 0, st>>>(pw, n, ldq_of(n), norms, csc, csc_cnt);
     CEVB_CHECK_LAUNCH("q_structure_kernel");
-    dim3 grid(n, B);
-    taylor_coeff_kernel<<<grid, 128, sizeof(double) * 6 * (size_t)npad, st>>>(
-        pw, csc, csc_cnt, norms, n, ldq_of(n), npad, tc);
+    dim3 grid((n + TCR - 1) / TCR, B);
+    const size_t csm = sizeof(double) * 6 * TCR * (size_t)npad;
+    CEVB_CHECK_CUDA(cudaFuncSetAttribute(taylor_coeff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)csm));
+    taylor_coeff_kernel<<<grid, 128, csm, st>>>(
+        pw, csc, csc_cnt, norms, n, ldq_of(n), npad, t_max, tc);
     CEVB_CHECK_LAUNCH("taylor_coeff_kernel");
     return 0;
 }

@@ -129,6 +129,8 @@ class LikelihoodEngine:
         self.h_level_child_off = np.ascontiguousarray(flat.level_child_off, dtype=np.int32)
         self.d_leaf_child = torch.as_tensor(flat.leaf_child, **i32)
         self.d_t_node = torch.as_tensor(flat.dist_eff, dtype=torch.float64, device=self.device)
+        tm = float(np.nanmax(flat.t_unique)) if flat.t_unique.size else 0.0
+        self.t_max = tm if np.isfinite(tm) and not np.isnan(flat.t_unique).any() else 0.0
         self.d_t_order = torch.as_tensor(np.argsort(-np.nan_to_num(flat.t_unique), kind="stable")
                                          .astype(np.int32), device=self.device)
         mat_bytes = 8 * self.n * self.ldp
@@ -235,7 +237,7 @@ class LikelihoodEngine:
         one = lambda t: _lib.ptr(t[k:])
         e0 = self._mark("prepare")
         _lib.check(lib.cevb_build_q(P(ws.params), nb, self.n, P(ws.pw), st), "cevb_build_q")
-        _lib.check(lib.cevb_taylor_prepare(P(ws.pw), nb, self.n, P(ws.norms), P(ws.csc),
+        _lib.check(lib.cevb_taylor_prepare(P(ws.pw), nb, self.n, self.t_max, P(ws.norms), P(ws.csc),
                                            P(ws.csc_cnt), P(ws.tc), st), "cevb_taylor_prepare")
         _lib.check(lib.cevb_expm_plan(P(ws.norms), _lib.ptr(self.d_t), nb, f.n_t, pps, P(ws.slot),
                                       Q(ws.worklist), Q(ws.work_s), one(ws.work_count), st),

@@ -114,7 +114,9 @@ int cevb_expm_branches_list(const double* pw, const double* norms, const uint16_
  * branch_params), so with the shift mu = max(0, -min_i Q_ii) (uniformisation: Q + mu I is
  * non-negative for a generator, so the series has no cancellation)
  *     expm(Q t) = e^{-mu t} sum_k t^k C_k,   C_k = (Q + mu I)^k / k!
- * with C_k formed once per vector.  cevb_taylor_prepare needs only slot 0 of pw (Q) and writes
+ * with C_k formed once per vector.  cevb_taylor_prepare needs only slot 0 of pw (Q); t_max > 0
+ * promises that no branch is longer than t_max, so only the chunks such a branch can need are
+ * formed (<= 0: all of them).  It writes
  *   norms[b][CEVB_NORM_ONE / _SHIFT / _SHIFTED] = ||Q_b||_1, mu_b, nu_b,
  *   the compressed-column structure csc / csc_cnt and
  *   tc [B][n][CEVB_TAYLOR_KC][n_pad][4]   (n_pad = n rounded up to 8; cevb_taylor_doubles(n)
@@ -134,7 +136,7 @@ size_t cevb_taylor_doubles(int n);
 /* 1 when cevb_taylor_matrices can keep two n x n matrices in shared memory (n <= 112 on B200);
  * larger orders use cevb_expm_branches_list for the pairs that need squarings */
 int cevb_taylor_matrices_supported(int n);
-int cevb_taylor_prepare(const double* pw, int B, int n, double* norms, uint16_t* csc,
+int cevb_taylor_prepare(const double* pw, int B, int n, double t_max, double* norms, uint16_t* csc,
                         uint8_t* csc_cnt, double* tc, void* stream);
 int cevb_expm_plan(const double* norms, const double* t, int B, int E, long long cap, int32_t* slot,
                    int32_t* worklist, int32_t* work_s, unsigned int* count, void* stream);

@@ -38,7 +38,7 @@ def _apply(rows, times, N, child_vectors=None, codes=None):
     st = _stream_ptr()
     _lib.check(lib.cevb_build_q(_lib.ptr(ws.params), B, n, _lib.ptr(ws.pw), st), "build_q")
     tc = torch.empty((B, lib.cevb_taylor_doubles(n)), dtype=torch.float64, device=dev)
-    _lib.check(lib.cevb_taylor_prepare(_lib.ptr(ws.pw), B, n, _lib.ptr(ws.norms), _lib.ptr(ws.csc),
+    _lib.check(lib.cevb_taylor_prepare(_lib.ptr(ws.pw), B, n, 0.0, _lib.ptr(ws.norms), _lib.ptr(ws.csc),
                                        _lib.ptr(ws.csc_cnt), _lib.ptr(tc), st), "taylor_prepare")
     ldp = ws.ldp
     t_node = torch.as_tensor(np.repeat(times, K), device=dev)
@@ -214,7 +214,7 @@ def _series_matrices(rows, times, N):
     ws.params.copy_(torch.as_tensor(rows, device=dev))
     st = _stream_ptr()
     _lib.check(lib.cevb_build_q(_lib.ptr(ws.params), B, n, _lib.ptr(ws.pw), st), "build_q")
-    _lib.check(lib.cevb_taylor_prepare(_lib.ptr(ws.pw), B, n, _lib.ptr(ws.norms), _lib.ptr(ws.csc),
+    _lib.check(lib.cevb_taylor_prepare(_lib.ptr(ws.pw), B, n, 0.0, _lib.ptr(ws.norms), _lib.ptr(ws.csc),
                                        _lib.ptr(ws.csc_cnt), _lib.ptr(ws.tc), st), "taylor_prepare")
     d_t = torch.as_tensor(times, device=dev)
     order = torch.as_tensor(np.argsort(-times, kind="stable").astype(np.int32), device=dev)

@@ -21,7 +21,7 @@ st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 ws = ExpmWorkspace(n, 1, B, dev, p_slots=1, n_nodes=1)
 ws.params.copy_(torch.as_tensor(rows, device=dev))
 lib.cevb_build_q(_lib.ptr(ws.params), B, n, _lib.ptr(ws.pw), st)
-lib.cevb_taylor_prepare(_lib.ptr(ws.pw), B, n, _lib.ptr(ws.norms), _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt),
+lib.cevb_taylor_prepare(_lib.ptr(ws.pw), B, n, 0.0, _lib.ptr(ws.norms), _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt),
                         _lib.ptr(ws.tc), st)
 torch.cuda.synchronize()
 nu, mu = float(ws.norms[0, 12]), float(ws.norms[0, 11])

@@ -48,6 +48,8 @@ for key in order:
     if key[0] == "apply":
         line.append(f"{sizes[key[1]]}:{acc[key]:.2f}")
 print("apply per launch (items:ms):", " ".join(line))
+print("combine per level (nodes:ms):", " ".join(f"{c}:{acc[k]:.3f}" for c, k in zip(
+    np.diff(flat.level_off).tolist(), [k for k in order if k[0] == "combine"])))
 print("totals ms:", {k: round(v, 2) for k, v in tot.items()})
 # un-instrumented wall time
 torch.cuda.synchronize()
