@@ -282,6 +282,7 @@ def run_ours(args):
     t_single = ev0.elapsed_time(ev1) * 1e-3 / reps1
 
     if rank != 0:
+        D.shutdown()
         return 0
 
     # ---- algorithmic work of the timed region
@@ -389,6 +390,7 @@ def run_ours(args):
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))
+    D.shutdown()
     return 0
 
 

@@ -14,5 +14,7 @@ from .ancestral_reconstruction import (  # noqa: F401
     ChromEvolOptimizer, StochasticMapper, perform_chromevol_analysis,
     calculate_model_selection_criteria)
 from .engine import LikelihoodEngine, params_to_row, rate_matrix, transition_matrices  # noqa: F401
+from .pipeline import (  # noqa: F401
+    ancestral_reconstruction, quantify_rearrangements_from_tree, write_ancestral_states_report)
 
 __version__ = "0.1.0"
