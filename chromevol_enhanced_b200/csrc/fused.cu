@@ -23,9 +23,6 @@
 // Branches with eta > 5.4 need squarings and therefore a materialised matrix: they are routed
 // (cevb_expm_plan) to the Pade kernel of expm.cu, whose P the combine kernel reads.
 #include <stdlib.h>
-#ifndef CEVB_EXP
-#define CEVB_EXP 0
-#endif
 
 #include "common.cuh"
 
@@ -327,6 +324,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -502,18 +502,26 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     __syncthreads();
 
     if (warp == NW) {
-        // ---- producer: one lane streams the (row, pass) tiles of the coefficient table
+        // ---- producer: one lane streams the (row, pass) tiles of the coefficient table.  The
+        // ring is only a few rows deep, so rows further ahead are pulled into L2 first
+        // (cp.async.bulk.prefetch.L2).
         if (lane != 0) return;
         const double* tcb = a.tc + (size_t)b * n * F_KC * npad * 4;
+        constexpr int PF_ROWS = 6;
+        const uint32_t row_bytes = (uint32_t)npad * 4 * sizeof(double);
+        // 97 <= n <= 104: the ck chunks a row needs are contiguous in the table and in the
+        // stage, so a row is ONE bulk copy
+        const bool contiguous = (npad == F_JT * 8);
+        for (int i = i_begin; i < min(i_end, i_begin + PF_ROWS); ++i)
+            bulk_prefetch_l2(tcb + (size_t)i * F_KC * npad * 4, row_bytes * (uint32_t)ck);
         int s = 0, use = 0;
         for (int i = i_begin; i < i_end; ++i) {
+            if (i + PF_ROWS < i_end)
+                bulk_prefetch_l2(tcb + (size_t)(i + PF_ROWS) * F_KC * npad * 4, row_bytes * (uint32_t)ck);
             for (int pass = 0; pass < npass; ++pass) {
-#if CEVB_EXP == 4 || CEVB_EXP == 5 || CEVB_EXP == 9
-                if (use > 0) return;
-#endif
                 if (use > 0) {
                     const uint32_t par = (uint32_t)((use - 1) & 1);
-                    while (!mbar_try_wait(&empty[s], par)) __nanosleep(64);
+                    while (!mbar_try_wait(&empty[s], par)) __nanosleep(32);
                 }
                 const int j0 = pass * F_JT * 8;
                 const int ncols = min(F_JT * 8, npad - j0);
@@ -521,8 +529,12 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
                 mbar_expect_tx(&full[s], bytes * (uint32_t)ck);
                 double* dst = Bs + (size_t)s * stage_doubles;
                 const double* src = tcb + ((size_t)i * F_KC * npad + j0) * 4;
-                for (int c = 0; c < ck; ++c)
-                    bulk_g2s(dst + (size_t)c * F_JT * 32, src + (size_t)c * npad * 4, bytes, &full[s]);
+                if (contiguous) {
+                    bulk_g2s(dst, src, bytes * (uint32_t)ck, &full[s]);
+                } else {
+                    for (int c = 0; c < ck; ++c)
+                        bulk_g2s(dst + (size_t)c * F_JT * 32, src + (size_t)c * npad * 4, bytes, &full[s]);
+                }
                 if (++s == ns) {
                     s = 0;
                     ++use;
@@ -611,10 +623,6 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     // end of a row: quad reduction and the two stores (the combine kernel forms d / r, AR:154)
     auto finish_row = [&](const int i_e) {
         if (EVAL) return;
-#if CEVB_EXP == 8 || CEVB_EXP == 9
-        if (rs0 == 1.2345e-300) a.w[i_e] = dt0;
-        return;
-#endif
         double r = rs0 + rs1, d = dt0 + dt1;
         r += __shfl_xor_sync(0xffffffffu, r, 1);
         d += __shfl_xor_sync(0xffffffffu, d, 1);
@@ -639,9 +647,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     for (int i = i_begin; i < i_end; ++i) {
         for (int pass = 0; pass < npass; ++pass) {
             const int njt = min(F_JT, nj - pass * F_JT);
-#if CEVB_EXP != 4 && CEVB_EXP != 5 && CEVB_EXP != 9
             mbar_wait(&full[s], par);
-#endif
             const double* Bq = Bs + (size_t)s * stage_doubles + lane;
             // Per chunk: the 13 B-fragment loads are issued back to back into 13 registers and
             // only then the 13 DMMAs (the compiler barriers keep ptxas from re-interleaving
@@ -661,15 +667,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
                     acc[jt][0] = 0.0;
                     acc[jt][1] = 0.0;
                     dmma884(acc[jt][0], acc[jt][1], av, bv[jt]);
-#if CEVB_EXP < 3 || CEVB_EXP == 8
                     if (have_prev) epi_tile(jt, p0, p1, i_prev, pass_prev, njt_prev);
-#else
-#if CEVB_EXP == 5 || CEVB_EXP == 6 || CEVB_EXP == 9
-                    if ((__double2hiint(p0) ^ __double2hiint(p1)) == 0x12345678) rs0 += 1.0;
-#else
-                    if (p0 == 1.2345e-300 || p1 == 1.2345e-300) rs0 += 1.0;
-#endif
-#endif
                 }
                 asm volatile("" ::: "memory");
             }
@@ -685,9 +683,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
             }
             // every shared-memory read of this stage has been consumed by an issued DMMA
             __syncwarp();
-#if CEVB_EXP != 4 && CEVB_EXP != 5 && CEVB_EXP != 9
             if (lane == 0) mbar_arrive(&empty[s]);
-#endif
             if (++s == ns) {
                 s = 0;
                 par ^= 1u;
