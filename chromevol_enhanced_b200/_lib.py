@@ -41,15 +41,16 @@ _PROTOTYPES = {
     "cevb_taylor_prepare": (_c.c_int, [c_dp, _c.c_int, _c.c_int, _c.c_double, c_dp, c_dp, c_dp, c_dp,
                                        _c.c_void_p]),
     "cevb_expm_plan": (_c.c_int, [c_dp, c_dp, _c.c_int, _c.c_int, _c.c_longlong, c_dp, c_dp, c_dp,
-                                  c_dp, _c.c_void_p]),
-    "cevb_taylor_matrices": (_c.c_int, [c_dp, c_dp, c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, c_dp,
-                                        c_dp, c_dp, _c.c_longlong, c_dp, c_dp, c_dp, _c.c_void_p]),
+                                  c_dp, c_dp, c_dp, c_dp, _c.c_void_p]),
+    "cevb_taylor_matrices": (_c.c_int, [c_dp, c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, c_dp,
+                                        c_dp, c_dp, _c.c_longlong, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                        c_dp, _c.c_void_p]),
     "cevb_taylor_apply": (_c.c_int, [c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, c_dp, _c.c_int,
                                      _c.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, _c.c_void_p]),
     "cevb_prune_fused": (_c.c_int, [c_dp, c_dp, c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                     _c.c_int, c_dp, _c.POINTER(_c.c_int32), _c.c_int, c_dp, c_dp,
                                     c_dp, c_dp, c_dp, _c.POINTER(_c.c_int32),
-                                    c_dp, _c.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                    c_dp, _c.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                     c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     "cevb_prune": (_c.c_int, [c_dp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, c_dp,
                               _c.POINTER(_c.c_int32), _c.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,

@@ -285,12 +285,23 @@ __global__ void __launch_bounds__(256) expm_plan_kernel(const double* __restrict
                                                         int32_t* __restrict__ slot,
                                                         int32_t* __restrict__ worklist,
                                                         int32_t* __restrict__ work_s,
-                                                        unsigned int* __restrict__ count) {
+                                                        unsigned int* __restrict__ count,
+                                                        int32_t* __restrict__ plan_nc,
+                                                        double* __restrict__ plan_tau,
+                                                        double* __restrict__ plan_a0) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M) return;
     const int b = (int)(idx / E), e = (int)(idx - (long long)b * E);
     const double* nr = norms + (size_t)b * CEVB_NNORM;
     const PairPlan pp = plan_pair(t[e], nr[CEVB_NORM_SHIFTED], nr[CEVB_NORM_SHIFT]);
+    if (plan_nc != nullptr) {
+        // the per-pair decision is scalar FP64 work with long dependency chains (exp, divisions):
+        // done here once, one thread per pair, instead of serially at the start of every CTA
+        plan_nc[idx] = pp.nc | (pp.kind << 8);
+        plan_tau[idx] = pp.tau;
+        plan_a0[idx] = pp.a0;
+    }
+    if (slot == nullptr) return;
     int s = -1;
     if (pp.kind == 2) {
         const unsigned int q = atomicAdd(count, 1u);
@@ -355,6 +366,12 @@ struct ApplyArgs {
     const int32_t* slot;
     double* X;
     int E;
+    // per-pair plan [B][E] from expm_plan_kernel: series length | kind << 8, (scaled) time and
+    // e^{-mu tau}; branch_of maps a child node to its row of the plan (NULL: the node itself)
+    const int32_t* plan_nc;
+    const double* plan_tau;
+    const double* plan_a0;
+    const int32_t* branch_of;
 };
 
 constexpr int APPLY_GENERAL = 0, APPLY_LEAF = 1, APPLY_EVAL = 2;
@@ -412,34 +429,34 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     double* Ls = As + (size_t)(EB / 8) * F_KC * 32;                           // [EB][ldl] (not LEAF)
     double* Bs = Ls + (LEAF ? 0 : (size_t)EB * ldl);                          // ring of row tiles
 
-    const double nu = a.norms[(size_t)b * CEVB_NNORM + CEVB_NORM_SHIFTED];
-    const double mu = a.norms[(size_t)b * CEVB_NNORM + CEVB_NORM_SHIFT];
     for (int x = tid; x < EB; x += blockDim.x) {
         const int e = e0 + x;
         int nc = 0, child = -1, code = -2;
         double tau = 0.0, a0 = 0.0;
         if (e < a.n_items && EVAL) {
             const int item = a.items[e];
-            const PairPlan pp = plan_pair(a.t_node[item], nu, mu);
-            if (pp.kind == 2) {
-                child = a.slot[(size_t)b * a.E + item];     // P slot of this pair (< 0: overflow)
+            const size_t pi = (size_t)b * a.E + item;
+            const int pn = a.plan_nc[pi];
+            if ((pn >> 8) == 2) {
+                child = a.slot[pi];                         // P slot of this pair (< 0: overflow)
                 if (child >= 0) {
-                    nc = pp.nc;
-                    tau = pp.tau;
-                    a0 = pp.a0;
+                    nc = pn & 0xff;
+                    tau = a.plan_tau[pi];
+                    a0 = a.plan_a0[pi];
                 }
             }
         } else if (e < a.n_items) {
             child = a.items[e];
             code = a.leaf_code[child];
-            const PairPlan pp = plan_pair(a.t_node[child], nu, mu);
-            if (pp.kind != 0) {
+            const size_t pi = (size_t)b * a.E + (a.branch_of ? a.branch_of[child] : child);
+            const int pn = a.plan_nc[pi];
+            if ((pn >> 8) != 0) {
                 // 1: t == 0 -> identity (AR:146-148); 2: scaling-and-squaring path
-                a.mode[(size_t)b * a.n_nodes + child] = (uint8_t)pp.kind;
+                a.mode[(size_t)b * a.n_nodes + child] = (uint8_t)(pn >> 8);
             } else {
-                nc = pp.nc;
-                tau = pp.tau;
-                a0 = pp.a0;
+                nc = pn & 0xff;
+                tau = a.plan_tau[pi];
+                a0 = a.plan_a0[pi];
             }
         }
         s_child[x] = child;
@@ -1020,8 +1037,16 @@ __global__ void __launch_bounds__(SQ_NT, 1) square_post_kernel(double* __restric
     }
 }
 
+struct PlanRef {
+    const int32_t* nc;
+    const double* tau;
+    const double* a0;
+    const int32_t* branch_of;
+    int E;
+};
+
 static int launch_apply(const double* tc, const double* norms, int B, int n, int n_nodes,
-                        const int32_t* items, int n_items, int leaf_only, const double* t_node,
+                        const int32_t* items, int n_items, int leaf_only, const PlanRef& plan,
                         const int32_t* leaf_code, const double* node_vec, double* w, double* wr,
                         uint8_t* mode, cudaStream_t st) {
     if (n_items <= 0 || B <= 0) return 0;
@@ -1031,11 +1056,12 @@ static int launch_apply(const double* tc, const double* norms, int B, int n, int
         return -1;
     }
     ApplyArgs a;
-    a.tc = tc; a.norms = norms; a.items = items; a.t_node = t_node; a.leaf_code = leaf_code;
+    a.tc = tc; a.norms = norms; a.items = items; a.t_node = nullptr; a.leaf_code = leaf_code;
     a.node_vec = node_vec; a.w = w; a.wr = wr; a.mode = mode;
     a.n_items = n_items; a.n = n; a.npad = round_up(n, 8); a.ldp = ldp_of(n); a.n_nodes = n_nodes;
     a.ldl = a.npad + ((a.npad % 16) == 0 ? 8 : 0);
-    a.slot = nullptr; a.X = nullptr; a.E = 0;
+    a.slot = nullptr; a.X = nullptr; a.E = plan.E;
+    a.plan_nc = plan.nc; a.plan_tau = plan.tau; a.plan_a0 = plan.a0; a.branch_of = plan.branch_of;
     const int rc = leaf_only ? launch_apply_shapes<APPLY_LEAF>(a, B, st)
                              : launch_apply_shapes<APPLY_GENERAL>(a, B, st);
     if (rc == 1) {
@@ -1076,13 +1102,14 @@ extern "C" int cevb_taylor_prepare(const double* pw, int B, int n, double t_max,
 
 extern "C" int cevb_expm_plan(const double* norms, const double* t, int B, int E, long long cap,
                               int32_t* slot, int32_t* worklist, int32_t* work_s, unsigned int* count,
-                              void* stream) {
+                              int32_t* plan_nc, double* plan_tau, double* plan_a0, void* stream) {
     if (B <= 0 || E <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    CEVB_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned int), st));
+    if (count != nullptr) CEVB_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned int), st));
     const long long M = (long long)B * E;
     expm_plan_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(norms, t, E, M, cap, slot, worklist,
-                                                                work_s, count);
+                                                                work_s, count, plan_nc, plan_tau,
+                                                                plan_a0);
     CEVB_CHECK_LAUNCH("expm_plan_kernel");
     return 0;
 }
@@ -1092,11 +1119,12 @@ extern "C" int cevb_taylor_matrices_supported(int n) {
     return (n >= 2 && n <= CEVB_MAX_N && square_smem_bytes(round_up(n, 8)) <= g_f_optin) ? 1 : 0;
 }
 
-extern "C" int cevb_taylor_matrices(const double* tc, const double* norms, const double* t,
-                                    const int32_t* t_order, int B, int E, int n,
-                                    const int32_t* slot, const int32_t* work_s,
-                                    const unsigned int* count, long long cap, double* P,
-                                    unsigned int* counter, int32_t* nan_count, void* stream) {
+extern "C" int cevb_taylor_matrices(const double* tc, const double* norms, const int32_t* t_order,
+                                    int B, int E, int n, const int32_t* slot,
+                                    const int32_t* work_s, const unsigned int* count, long long cap,
+                                    const int32_t* plan_nc, const double* plan_tau,
+                                    const double* plan_a0, double* P, unsigned int* counter,
+                                    int32_t* nan_count, void* stream) {
     if (B <= 0 || E <= 0 || cap <= 0) return 0;
     if (B > 65535) {
         set_error("cevb_taylor_matrices: B=%d exceeds one launch; chunk the batch", B);
@@ -1109,11 +1137,12 @@ extern "C" int cevb_taylor_matrices(const double* tc, const double* norms, const
     }
     cudaStream_t st = (cudaStream_t)stream;
     ApplyArgs a;
-    a.tc = tc; a.norms = norms; a.items = t_order; a.t_node = t; a.leaf_code = nullptr;
+    a.tc = tc; a.norms = norms; a.items = t_order; a.t_node = nullptr; a.leaf_code = nullptr;
     a.node_vec = nullptr; a.w = nullptr; a.wr = nullptr; a.mode = nullptr;
     a.n_items = E; a.n = n; a.npad = round_up(n, 8); a.ldp = ldp_of(n); a.n_nodes = 0;
     a.ldl = 0;
     a.slot = slot; a.X = P; a.E = E;
+    a.plan_nc = plan_nc; a.plan_tau = plan_tau; a.plan_a0 = plan_a0; a.branch_of = nullptr;
     int rc = launch_apply_shapes<APPLY_EVAL>(a, B, st);
     if (rc == 1) {
         set_error("cevb_taylor_matrices: n=%d does not fit in shared memory", n);
@@ -1145,8 +1174,27 @@ extern "C" int cevb_taylor_apply(const double* tc, const double* norms, int B, i
         set_error("cevb_taylor_apply: B=%d exceeds one launch; chunk the batch", B);
         return -1;
     }
-    return launch_apply(tc, norms, B, n, n_nodes, items, n_items, leaf_only, t_node, leaf_code,
-                        node_vec, w, wr, mode, (cudaStream_t)stream);
+    if (B <= 0 || n_items <= 0) return 0;
+    // stand-alone call: the per-pair plan is indexed by node and lives in stream-ordered scratch
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t M = (size_t)B * n_nodes;
+    int32_t* p_nc = nullptr;
+    double* p_tau = nullptr;
+    double* p_a0 = nullptr;
+    CEVB_CHECK_CUDA(cudaMallocAsync((void**)&p_nc, M * sizeof(int32_t), st));
+    CEVB_CHECK_CUDA(cudaMallocAsync((void**)&p_tau, M * sizeof(double), st));
+    CEVB_CHECK_CUDA(cudaMallocAsync((void**)&p_a0, M * sizeof(double), st));
+    int rc = cevb_expm_plan(norms, t_node, B, n_nodes, 0, nullptr, nullptr, nullptr, nullptr, p_nc,
+                            p_tau, p_a0, stream);
+    if (rc == 0) {
+        const PlanRef plan = {p_nc, p_tau, p_a0, nullptr, n_nodes};
+        rc = launch_apply(tc, norms, B, n, n_nodes, items, n_items, leaf_only, plan, leaf_code,
+                          node_vec, w, wr, mode, st);
+    }
+    cudaFreeAsync(p_nc, st);
+    cudaFreeAsync(p_tau, st);
+    cudaFreeAsync(p_a0, st);
+    return rc;
 }
 
 extern "C" int cevb_prune_fused(const double* tc, const double* norms, const double* P,
@@ -1155,8 +1203,10 @@ extern "C" int cevb_prune_fused(const double* tc, const double* norms, const dou
                                 int n_levels, const int32_t* child_off, const int32_t* child_idx,
                                 const int32_t* branch_of, const int32_t* leaf_code,
                                 const int32_t* level_child, const int32_t* level_child_off_host,
-                                const int32_t* leaf_child, int n_leaf_child, const double* t_node,
-                                const double* root_freq, double* node_vec, double* w, double* wr,
+                                const int32_t* leaf_child, int n_leaf_child,
+                                const int32_t* plan_nc, const double* plan_tau,
+                                const double* plan_a0, const double* root_freq, double* node_vec,
+                                double* w, double* wr,
                                 uint8_t* mode, double* logl, int32_t* rescales,
                                 int level_begin, int level_end, int stages, void* stream) {
     if (B <= 0) return 0;
@@ -1166,6 +1216,7 @@ extern "C" int cevb_prune_fused(const double* tc, const double* norms, const dou
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int ldp = ldp_of(n);
+    const PlanRef plan = {plan_nc, plan_tau, plan_a0, branch_of, E};
     if (stages & CEVB_FUSED_INIT) {
         CEVB_CHECK_CUDA(cudaMemsetAsync(rescales, 0, sizeof(int32_t) * (size_t)B, st));
         CEVB_CHECK_CUDA(cudaMemsetAsync(mode, 0, (size_t)B * n_nodes, st));
@@ -1179,7 +1230,7 @@ extern "C" int cevb_prune_fused(const double* tc, const double* norms, const dou
     }
     if (stages & CEVB_FUSED_LEAVES) {
         // branches above observed leaves depend on nothing below them: all levels in one launch
-        const int rc = launch_apply(tc, norms, B, n, n_nodes, leaf_child, n_leaf_child, 1, t_node,
+        const int rc = launch_apply(tc, norms, B, n, n_nodes, leaf_child, n_leaf_child, 1, plan,
                                     leaf_code, node_vec, w, wr, mode, st);
         if (rc != 0) return rc;
     }
@@ -1191,7 +1242,7 @@ extern "C" int cevb_prune_fused(const double* tc, const double* norms, const dou
         if (cnt <= 0) continue;
         if (stages & CEVB_FUSED_APPLY) {
             const int c0 = level_child_off_host[lv], c1 = level_child_off_host[lv + 1];
-            const int rc = launch_apply(tc, norms, B, n, n_nodes, level_child + c0, c1 - c0, 0, t_node,
+            const int rc = launch_apply(tc, norms, B, n, n_nodes, level_child + c0, c1 - c0, 0, plan,
                                         leaf_code, node_vec, w, wr, mode, st);
             if (rc != 0) return rc;
         }

@@ -73,6 +73,9 @@ class ExpmWorkspace:
         if n_nodes:
             self.tc = torch.empty((cap, lib.cevb_taylor_doubles(n)), **f64)
             self.slot = torch.empty((cap, n_t), dtype=torch.int32, device=device)
+            self.plan_nc = torch.empty((cap, n_t), dtype=torch.int32, device=device)
+            self.plan_tau = torch.empty((cap, n_t), **f64)
+            self.plan_a0 = torch.empty((cap, n_t), **f64)
             self.worklist = torch.empty(max(self.p_slots, 1), dtype=torch.int32, device=device)
             self.work_s = torch.zeros(max(self.p_slots, 1), dtype=torch.int32, device=device)
             self.nan_count = torch.zeros(16, dtype=torch.int32, device=device)
@@ -240,14 +243,15 @@ class LikelihoodEngine:
         _lib.check(lib.cevb_taylor_prepare(P(ws.pw), nb, self.n, self.t_max, P(ws.norms), P(ws.csc),
                                            P(ws.csc_cnt), P(ws.tc), st), "cevb_taylor_prepare")
         _lib.check(lib.cevb_expm_plan(P(ws.norms), _lib.ptr(self.d_t), nb, f.n_t, pps, P(ws.slot),
-                                      Q(ws.worklist), Q(ws.work_s), one(ws.work_count), st),
-                   "cevb_expm_plan")
+                                      Q(ws.worklist), Q(ws.work_s), one(ws.work_count), P(ws.plan_nc),
+                                      P(ws.plan_tau), P(ws.plan_a0), st), "cevb_expm_plan")
         e1 = self._mark("prepare", e0)
         if self.squaring == "series":
             _lib.check(lib.cevb_taylor_matrices(
-                P(ws.tc), P(ws.norms), _lib.ptr(self.d_t), _lib.ptr(self.d_t_order), nb, f.n_t,
-                self.n, P(ws.slot), Q(ws.work_s), one(ws.work_count), pps, Q(ws.P),
-                one(ws.counter), one(ws.nan_count), st), "cevb_taylor_matrices")
+                P(ws.tc), P(ws.norms), _lib.ptr(self.d_t_order), nb, f.n_t, self.n, P(ws.slot),
+                Q(ws.work_s), one(ws.work_count), pps, P(ws.plan_nc), P(ws.plan_tau),
+                P(ws.plan_a0), Q(ws.P), one(ws.counter), one(ws.nan_count), st),
+                "cevb_taylor_matrices")
         else:
             # Pade-13 + scaling and squaring (the scipy algorithm) for the listed pairs
             _lib.check(lib.cevb_expm_prepare(P(ws.pw), nb, self.n, P(ws.norms), P(ws.csc),
@@ -266,8 +270,8 @@ class LikelihoodEngine:
                 _lib.ptr(self.d_child_off), _lib.ptr(self.d_child_idx), _lib.ptr(self.d_branch_of),
                 _lib.ptr(self.d_leaf_code), _lib.ptr(self.d_level_child),
                 self.h_level_child_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
-                _lib.ptr(self.d_leaf_child), int(f.leaf_child.size), _lib.ptr(self.d_t_node),
-                _lib.ptr(d_root_freq), P(self._node_vec), P(ws.w), P(ws.wr), P(ws.mode),
+                _lib.ptr(self.d_leaf_child), int(f.leaf_child.size), P(ws.plan_nc),
+                P(ws.plan_tau), P(ws.plan_a0), _lib.ptr(d_root_freq), P(self._node_vec), P(ws.w), P(ws.wr), P(ws.mode),
                 P(self._logl), P(self._rescales), l0, l1, stages, st), "cevb_prune_fused")
 
         leafvec = FUSED_LEAFVEC if self.want_node_vectors else 0

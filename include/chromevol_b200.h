@@ -127,7 +127,9 @@ int cevb_expm_branches_list(const double* pw, const double* norms, const uint16_
  * that (nu t above about 7), which needs scaling and squaring and therefore a materialised
  * matrix: slot [B][E] = position in worklist (-1 = fused path, -2 = list overflow),
  * work_s [cap] = squarings of that position (may be NULL), *count = pairs found (may exceed
- * cap; the caller then re-plans).
+ * cap; the caller then re-plans).  It also records the decision per pair for the kernels:
+ * plan_nc [B][E] = series terms | kind << 8 (kind 0 fused, 1 identity, 2 materialised),
+ * plan_tau [B][E] = t 2^-s, plan_a0 [B][E] = e^{-mu t 2^-s}.
  * cevb_taylor_matrices fills the P slots of a plan: the series at t 2^-s for all listed pairs
  * of a vector at once (tensor cores, t_order = branch-length indices sorted by decreasing t),
  * then s squarings and the AR:153-159 post-processing per matrix in shared memory.
@@ -139,10 +141,12 @@ int cevb_taylor_matrices_supported(int n);
 int cevb_taylor_prepare(const double* pw, int B, int n, double t_max, double* norms, uint16_t* csc,
                         uint8_t* csc_cnt, double* tc, void* stream);
 int cevb_expm_plan(const double* norms, const double* t, int B, int E, long long cap, int32_t* slot,
-                   int32_t* worklist, int32_t* work_s, unsigned int* count, void* stream);
-int cevb_taylor_matrices(const double* tc, const double* norms, const double* t,
-                         const int32_t* t_order, int B, int E, int n, const int32_t* slot,
-                         const int32_t* work_s, const unsigned int* count, long long cap, double* P,
+                   int32_t* worklist, int32_t* work_s, unsigned int* count, int32_t* plan_nc,
+                   double* plan_tau, double* plan_a0, void* stream);
+int cevb_taylor_matrices(const double* tc, const double* norms, const int32_t* t_order, int B, int E,
+                         int n, const int32_t* slot, const int32_t* work_s,
+                         const unsigned int* count, long long cap, const int32_t* plan_nc,
+                         const double* plan_tau, const double* plan_a0, double* P,
                          unsigned int* counter, int32_t* nan_count, void* stream);
 
 /* ---- (2d+3) fused transition-probability x child-vector product, AR:136-166 + AR:237 without
@@ -168,7 +172,8 @@ int cevb_taylor_apply(const double* tc, const double* norms, int B, int n, int n
  *                             level of their parent (any order inside a level; longest
  *                             branches first packs the work best),
  *   level_child_off [n_levels+1] HOST offsets into level_child,
- *   t_node [n_nodes]          effective branch length above every node,
+ *   plan_nc / plan_tau / plan_a0 [B][E] the per-pair plan written by cevb_expm_plan (row
+ *                             branch_of[child] belongs to the branch above a child),
  *   P / slot                  materialised matrices and slot map from cevb_expm_plan +
  *                             cevb_expm_branches_list (E = row length of slot),
  *   w, wr [B][n_nodes][ldp], mode [B][n_nodes]   scratch.
@@ -182,8 +187,9 @@ int cevb_prune_fused(const double* tc, const double* norms, const double* P, con
                      const int32_t* level_off_host, int n_levels, const int32_t* child_off,
                      const int32_t* child_idx, const int32_t* branch_of, const int32_t* leaf_code,
                      const int32_t* level_child, const int32_t* level_child_off_host,
-                     const int32_t* leaf_child, int n_leaf_child, const double* t_node,
-                     const double* root_freq, double* node_vec, double* w, double* wr,
+                     const int32_t* leaf_child, int n_leaf_child, const int32_t* plan_nc,
+                     const double* plan_tau, const double* plan_a0, const double* root_freq,
+                     double* node_vec, double* w, double* wr,
                      uint8_t* mode, double* logl, int32_t* rescales, int level_begin, int level_end,
                      int stages, void* stream);
 

@@ -220,12 +220,14 @@ def _series_matrices(rows, times, N):
     order = torch.as_tensor(np.argsort(-times, kind="stable").astype(np.int32), device=dev)
     _lib.check(lib.cevb_expm_plan(_lib.ptr(ws.norms), _lib.ptr(d_t), B, E, B * E, _lib.ptr(ws.slot),
                                   _lib.ptr(ws.worklist), _lib.ptr(ws.work_s), _lib.ptr(ws.work_count),
+                                  _lib.ptr(ws.plan_nc), _lib.ptr(ws.plan_tau), _lib.ptr(ws.plan_a0),
                                   st), "plan")
     ws.P.fill_(float("nan"))
-    _lib.check(lib.cevb_taylor_matrices(_lib.ptr(ws.tc), _lib.ptr(ws.norms), _lib.ptr(d_t),
-                                        _lib.ptr(order), B, E, n, _lib.ptr(ws.slot), _lib.ptr(ws.work_s),
-                                        _lib.ptr(ws.work_count), B * E, _lib.ptr(ws.P),
-                                        _lib.ptr(ws.counter), _lib.ptr(ws.nan_count), st), "matrices")
+    _lib.check(lib.cevb_taylor_matrices(_lib.ptr(ws.tc), _lib.ptr(ws.norms), _lib.ptr(order), B, E, n,
+                                        _lib.ptr(ws.slot), _lib.ptr(ws.work_s), _lib.ptr(ws.work_count),
+                                        B * E, _lib.ptr(ws.plan_nc), _lib.ptr(ws.plan_tau),
+                                        _lib.ptr(ws.plan_a0), _lib.ptr(ws.P), _lib.ptr(ws.counter),
+                                        _lib.ptr(ws.nan_count), st), "matrices")
     torch.cuda.synchronize()
     cnt = int(ws.work_count[0])
     return (ws.P[:cnt, :, :n].cpu().numpy(), ws.slot.cpu().numpy(), ws.work_s[:cnt].cpu().numpy(),

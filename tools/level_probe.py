@@ -16,7 +16,8 @@ tree = synthetic.random_tree(1000, seed=1)
 counts = synthetic.simulate_tip_counts(tree, 100, seed=2)
 flat = FlatTree(tree, counts, 100)
 rows = torch.as_tensor(synthetic.random_param_rows(B, seed=4), device="cuda")
-eng = LikelihoodEngine(flat, max_workspace_bytes=48 << 30)
+NS = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+eng = LikelihoodEngine(flat, max_workspace_bytes=48 << 30, n_streams=NS)
 for _ in range(2):
     eng.log_likelihood(rows)
 torch.cuda.synchronize()
