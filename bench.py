@@ -281,6 +281,7 @@ def run_ours(args):
     barrier()
     t_single = ev0.elapsed_time(ev1) * 1e-3 / reps1
 
+    extras = run_extras(dev, rank, world) if args.extras else None
     if rank != 0:
         D.shutdown()
         return 0
@@ -389,9 +390,72 @@ def run_ours(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if extras is not None:
+        line["extras"] = extras
     print(json.dumps(line))
     D.shutdown()
     return 0
+
+
+def run_extras(dev, rank, world):
+    """Side measurements for the other BASELINE configs (not the headline metric):
+    configs[4] stochastic mapping replicates/s on the 1,000-taxon tree (replicates sharded over
+    ranks, disjoint Philox counters) and configs[3]'s building block, one log-likelihood
+    evaluation on a 10,000-taxon tree with N=256."""
+    import torch
+    from chromevol_enhanced_b200 import mapper, synthetic
+    from chromevol_enhanced_b200 import distributed as D
+    from chromevol_enhanced_b200.engine import LikelihoodEngine
+    from chromevol_enhanced_b200.flatten import FlatTree
+    out = {}
+    tree = synthetic.random_tree(N_TAXA, seed=TREE_SEED)
+    flat = FlatTree(tree, {}, MAX_CHR)
+    root = np.zeros(MAX_CHR + 1)
+    root[20] = 1.0
+    reps = 1_000_000
+    lo, hi = D.shard_bounds(reps, rank, world)
+    row = synthetic.default_param_row()
+    mapper.simulate(flat, row, MAX_CHR + 1, root, reps, 7, rep_begin=lo, rep_end=min(hi, lo + 4096),
+                    return_device=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    hist, sums, n_events = mapper.simulate(flat, row, MAX_CHR + 1, root, reps, 7, rep_begin=lo, rep_end=hi,
+                                           return_device=True)
+    e1.record()
+    torch.cuda.synchronize()
+    t = D.max_across_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+    ev = D.sum_across_ranks(n_events.to(torch.float64)).item() if world > 1 else float(n_events.item())
+    out["stochastic_mapping"] = {"workload": "BASELINE configs[4]: 1e6 replicates, 1,000-taxon tree, N=100, default rates",
+                                 "replicates_per_s": reps / t, "events_per_s": ev / t,
+                                 "branch_visits_per_s": reps * flat.n_branches / t, "seconds": t}
+    # configs[3] building block: one evaluation (and a 9-point finite-difference batch) at N=256
+    big = synthetic.random_tree(10_000, seed=11)
+    rng = np.random.default_rng(12)      # tip counts: seeded integers (simulating them down the
+    counts = {leaf.name: int(c) for leaf, c in      # tree would cost 20k scipy expm calls at n=257)
+              zip(big.get_leaves(), rng.integers(25, 60, size=10_000))}
+    fl = FlatTree(big, counts, 256)
+    eng = LikelihoodEngine(fl, device=dev, max_workspace_bytes=64 << 30)
+    eng.want_node_vectors = False
+    res = {}
+    for nb in (1, 9):
+        rows = np.tile(synthetic.default_param_row(), (nb, 1))
+        rows[:, 0] *= 1.0 + 1e-3 * np.arange(nb)
+        d = torch.as_tensor(rows, device=dev)
+        eng.log_likelihood(d)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            ll = eng.log_likelihood(d)
+        e1.record()
+        torch.cuda.synchronize()
+        res[f"batch_{nb}_ms"] = e0.elapsed_time(e1) / 3
+    res["logL"] = float(ll[0])
+    res["workload"] = ("BASELINE configs[3] building block: 10,000-taxon tree, N=256 (n=257, 19,998 branches), "
+                       "default rates; one evaluation and the 9-point gradient batch of one L-BFGS-B step")
+    res["squaring_path"] = eng.squaring
+    out["model_selection_unit"] = res
+    return out
 
 
 def main():
@@ -403,6 +467,9 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="parameter vectors per GPU per step")
     ap.add_argument("--workspace-gb", type=int, default=48)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--extras", action="store_true",
+                    help="also time the stochastic mapper (configs[4]) and an N=256 / 10,000-taxon "
+                         "evaluation (configs[3]); adds about a minute")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
