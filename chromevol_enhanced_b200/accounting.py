@@ -5,6 +5,7 @@ from __future__ import annotations
 import numpy as np
 
 KC = 10              # CEVB_TAYLOR_KC
+TRUNC = 1e-17        # CEVB_TAYLOR_TRUNC
 
 
 def taylor_ncoef(x, mut):
@@ -20,7 +21,7 @@ def taylor_ncoef(x, mut):
         sc = np.exp(-mut)
         for k in range(1, 4 * KC):
             term = term * (x / (k + 1))
-            ok = (~done) & ((k + 2) > x) & (term / (1.0 - x / (k + 2)) * sc <= 1e-18)
+            ok = (~done) & ((k + 2) > x) & (term / (1.0 - x / (k + 2)) * sc <= TRUNC)
             out[ok] = k + 1
             done |= ok
     return out

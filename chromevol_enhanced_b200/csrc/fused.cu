@@ -30,13 +30,14 @@ namespace cevb {
 
 constexpr int F_KC = CEVB_TAYLOR_KC;       // chunks of 4 series coefficients (degrees 0..39)
 constexpr int F_JT = 13;                   // 8-column tiles per pass (104 columns)
+constexpr double F_TRUNC = CEVB_TAYLOR_TRUNC;  // truncation bound of the series (absolute, entries <= 1)
 
 // The series is summed for the SHIFTED matrix (uniformisation): with mu = max(0, -min_i Q_ii),
 //     expm(Q t) = e^{-mu t} sum_k t^k C_k,   C_k = (Q + mu I)^k / k!.
 // For a generator Q + mu I is entrywise non-negative, so the sum has no cancellation and its
 // norm nu = min(||Q + mu I||_1, ||Q + mu I||_inf) is about half of ||Q||_1.
 // Number of series coefficients (degree + 1) so that the truncation bound
-//     x^(K+1)/(K+1)! / (1 - x/(K+2)) * e^{-mu t} <= 1e-18,   x = nu t;
+//     x^(K+1)/(K+1)! / (1 - x/(K+2)) * e^{-mu t} <= 1e-17 (a tenth of the unit roundoff),   x = nu t;
 // a result above 4 * F_KC means the coefficient table is too short (scale and square).
 __host__ __device__ inline int taylor_ncoef(double x, double mut) {
     if (!(x > 0.0)) return 1;
@@ -44,7 +45,7 @@ __host__ __device__ inline int taylor_ncoef(double x, double mut) {
     double term = x;  // x^k / k!
     for (int k = 1; k < 4 * F_KC; ++k) {
         term *= x / (double)(k + 1);  // x^(k+1) / (k+1)!
-        if ((double)(k + 2) > x && term / (1.0 - x / (double)(k + 2)) * sc <= 1e-18) return k + 1;
+        if ((double)(k + 2) > x && term / (1.0 - x / (double)(k + 2)) * sc <= F_TRUNC) return k + 1;
     }
     return 4 * F_KC + 1;
 }
@@ -844,6 +845,128 @@ __global__ void __launch_bounds__(CT) combine_level_kernel(
     }
 }
 
+// Same, one WARP per (parent node, vector) for n <= 128: four entries per lane in registers, warp
+// shuffles instead of block barriers, a quarter of the CTAs.  The level kernels are tiny, so their
+// cost is CTA scheduling and barrier latency rather than bytes.
+__global__ void __launch_bounds__(128) combine_level_warp_kernel(
+    const double* __restrict__ w, const double* __restrict__ wr, const uint8_t* __restrict__ mode,
+    const double* __restrict__ P, const int32_t* __restrict__ slot, int E, int n, int ldp,
+    int n_nodes, int root, int n_level, int B, const int32_t* __restrict__ level_nodes,
+    const int32_t* __restrict__ child_off, const int32_t* __restrict__ child_idx,
+    const int32_t* __restrict__ branch_of, const int32_t* __restrict__ leaf_code,
+    const double* __restrict__ root_freq, double* __restrict__ node_vec, double* __restrict__ logl,
+    int32_t* __restrict__ rescales) {
+    const int lane = threadIdx.x & 31;
+    const long long task = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (task >= (long long)n_level * B) return;
+    const int b = (int)(task / n_level);
+    const int node = level_nodes[task - (long long)b * n_level];
+    double v[4] = {1.0, 1.0, 1.0, 1.0};  // AR:219; entry lane + 32 k
+    int nres = 0;
+    const double unif = 1.0 / (double)n;
+    const int c_begin = child_off[node], c_end = child_off[node + 1];
+    for (int ci = c_begin; ci < c_end; ++ci) {
+        const int child = child_idx[ci];
+        const int code = leaf_code[child];
+        int md = mode[(size_t)b * n_nodes + child];
+        const double* cv = node_vec + ((size_t)b * n_nodes + child) * ldp;
+        double x[4];
+        if (md == 0) {
+            const double* wv = w + ((size_t)b * n_nodes + child) * ldp;
+            const double* rv = wr + ((size_t)b * n_nodes + child) * ldp;
+            int bad = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = lane + 32 * k;
+                x[k] = 1.0;
+                if (i < n) {
+                    const double r = rv[i];
+                    bad |= !(fabs(r) < INFINITY);   // NaN / inf in P -> identity (AR:156-159)
+                    x[k] = wv[i] / r;
+                }
+            }
+            if (__any_sync(0xffffffffu, bad)) md = 1;
+        }
+        if (md == 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = lane + 32 * k;
+                x[k] = (i < n) ? ((code >= 0) ? (i == code ? 1.0 : 0.0) : (code == -1 ? unif : cv[i])) : 1.0;
+            }
+        } else if (md == 2) {
+            long long sl = slot[(size_t)b * E + branch_of[child]];
+            if (sl < 0) sl = 0;  // work-list overflow: the host discards this pass and re-runs
+            const double* Pm = P + (size_t)sl * n * ldp;
+            if (code >= 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = lane + 32 * k;
+                    x[k] = (i < n) ? Pm[(size_t)i * ldp + code] : 1.0;
+                }
+            } else {
+                double l[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = lane + 32 * k;
+                    l[k] = (j < n) ? ((code == -1) ? unif : cv[j]) : 0.0;
+                    x[k] = 1.0;
+                }
+                for (int i0 = 0; i0 < n; i0 += 4) {   // four rows in flight
+                    double a[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const double* row = Pm + (size_t)min(i0 + r, n - 1) * ldp;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int j = lane + 32 * k;
+                            if (j < n) a[r] = fma(row[j], l[k], a[r]);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const double sum = warp_sum(a[r]);
+                        const int i = i0 + r;
+                        if (i < n && (i & 31) == lane) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if ((i >> 5) == k) x[k] = sum;
+                        }
+                    }
+                }
+            }
+        }
+        double part = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] *= x[k];                                   // AR:237-238
+            if (lane + 32 * k < n) part += v[k];
+        }
+        const double s = warp_sum(part);                    // AR:241
+        if (s > 0.0 && s < 1e-100) {                        // AR:242-243
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = v[k] / s;
+            ++nres;
+        }
+    }
+    double* out = node_vec + ((size_t)b * n_nodes + node) * ldp;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int j = lane + 32 * k;
+        if (j < ldp) out[j] = (j < n) ? v[k] : 0.0;
+    }
+    if (lane == 0 && nres) atomicAdd(&rescales[b], nres);
+    if (node == root) {
+        double part = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = lane + 32 * k;
+            if (j < n) part += v[k] * root_freq[j];         // AR:268
+        }
+        const double L = warp_sum(part);
+        if (lane == 0) logl[b] = (L <= 0.0) ? -INFINITY : log(L);   // AR:270-272
+    }
+}
+
 // leaf vectors: one-hot at the observed count, uniform 1/n for missing data (AR:201-214)
 __global__ void __launch_bounds__(128) leaf_init_fused_kernel(int n, int ldp, int n_nodes,
                                                               const int32_t* __restrict__ leaf_code,
@@ -1246,7 +1369,17 @@ extern "C" int cevb_prune_fused(const double* tc, const double* norms, const dou
                                         leaf_code, node_vec, w, wr, mode, st);
             if (rc != 0) return rc;
         }
-        if (stages & CEVB_FUSED_COMBINE) {
+        // wide levels: one warp per (node, vector) -- a quarter of the CTAs and no block
+        // barriers; narrow levels keep the block kernel, whose four warps share the (rare but
+        // long) mat-vec of a materialised P
+        if ((stages & CEVB_FUSED_COMBINE) && n <= 128 && cnt >= 100) {
+            const long long tasks = (long long)cnt * B;
+            combine_level_warp_kernel<<<(unsigned)((tasks + 3) / 4), 128, 0, st>>>(
+                w, wr, mode, P, slot, E, n, ldp, n_nodes, root, cnt, B,
+                level_nodes + level_off_host[lv], child_off, child_idx, branch_of, leaf_code,
+                root_freq, node_vec, logl, rescales);
+            CEVB_CHECK_LAUNCH("combine_level_warp_kernel");
+        } else if (stages & CEVB_FUSED_COMBINE) {
             dim3 grid(cnt, B);
             combine_level_kernel<<<grid, CT, csmem, st>>>(
                 w, wr, mode, P, slot, E, n, ldp, n_nodes, root, level_nodes + level_off_host[lv],
