@@ -157,6 +157,11 @@ class LikelihoodEngine:
         # leaf rows of node_vec are outputs only; batched logL callers (bench, optimiser) switch
         # them off, the drop-in classes read node vectors and keep them on
         self.want_node_vectors = True
+        # small batches (one evaluation, the 9 points of a finite-difference gradient) are launch-
+        # bound: about 50 kernels of a few microseconds each.  Their launch sequence is captured
+        # once per batch size into a CUDA graph and replayed.
+        self.graph_max_batch = 32
+        self._graphs = {}
         self.chunk = int(chunk)
         self.overflow_events = 0
         self._ws = None
@@ -174,6 +179,7 @@ class LikelihoodEngine:
             return
         self._ws = None
         self._node_vec = None
+        self._graphs = {}            # captured graphs hold pointers into the old workspace
         if self.path == "fused":
             slots = int(min(max(cap, self.n_streams) * self.flat.n_t,
                             max(self.p_budget // self.mat_bytes, self.n_streams * self.flat.n_t)))
@@ -369,6 +375,11 @@ class LikelihoodEngine:
             d_params = d_params[None, :]
         B = d_params.shape[0]
         d_root = root_freq if torch.is_tensor(root_freq) else self.root_freq_tensor(root_freq)
+        if (check_growth and 0 < B <= min(self.graph_max_batch, self.chunk) and self.path == "fused"
+                and self.squaring == "series" and self.stage_events is None and not self.keep_info):
+            out = self._graph_log_likelihood(d_params, d_root)
+            if out is not None:
+                return out
         out = torch.empty(B, dtype=torch.float64, device=self.device)
         self.rescale_counts = torch.zeros(B, dtype=torch.int32, device=self.device)
         self._ensure(min(self.chunk, B))
@@ -403,6 +414,52 @@ class LikelihoodEngine:
         self.n_chunks = (B + step - 1) // step
         self.last_batch = B
         return out
+
+    def _graph_log_likelihood(self, d_params, d_root):
+        """Small batch through a captured CUDA graph; None when the captured run has to be redone
+        eagerly (work-list overflow)."""
+        B = d_params.shape[0]
+        self._ensure(min(self.chunk, max(B, 1)))
+        key = (B, bool(self.want_node_vectors))
+        entry = self._graphs.get(key)
+        cur = torch.cuda.current_stream()
+        if entry is None:
+            f64 = dict(dtype=torch.float64, device=self.device)
+            sp = torch.zeros((B, 9), **f64)
+            sr = torch.zeros(self.n, **f64)
+            flags = torch.zeros(2, dtype=torch.bool, device=self.device)
+            sp.copy_(d_params)
+            sr.copy_(d_root)
+
+            def body():
+                self._growth_flag = torch.zeros((), dtype=torch.bool, device=self.device)
+                self._overflow_flag = torch.zeros((), dtype=torch.bool, device=self.device)
+                self._materialised = torch.zeros((), dtype=torch.int64, device=self.device)
+                self._run_chunk(sp, sr, 0)
+                flags.copy_(torch.stack([self._growth_flag, self._overflow_flag]))
+
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):          # warm-up outside capture (function attributes,
+                body()                             # allocator) as CUDA graph capture requires
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+            entry = (graph, sp, sr, flags)
+            self._graphs[key] = entry
+        graph, sp, sr, flags = entry
+        sp.copy_(d_params)
+        sr.copy_(d_root)
+        graph.replay()
+        if bool(flags[1].item()):
+            self.overflow_events += 1
+            return None
+        self.rescale_counts = self._rescales[:B].clone()
+        self.n_chunks = 1
+        self.last_batch = B
+        return self._logl[:B].clone()
 
     def node_vectors(self, which=0):
         """Conditional-likelihood vectors (n_nodes, n) of vector `which` of the last chunk."""
