@@ -62,6 +62,52 @@ def sharded_log_likelihood(evaluate, params_rows):
     return all_gather_ragged(local, params_rows.shape[0], world)
 
 
+def chromevol_model_configurations():
+    """Candidate set for model selection beyond the reference's two (SURVEY.md section 8(a) notes):
+    rate subsets mirroring ChromEvol's named models.  Each entry is an ordinary
+    `model_configurations` item of calculate_model_selection_criteria (AR:737-812), so every
+    candidate is checkable with the same oracle."""
+    zero = dict(gain=0.1, loss=0.1, dupl=0, demidupl_gain=0, demidupl_loss=0, base_number_gain=0,
+                base_number_loss=0, linear_rate=0)
+    def cfg(name, free, **init):
+        return {'name': name, 'initial_params': dict(zero, **init), 'params_to_optimize': free}
+    return [
+        cfg('GainLossOnly', ['gain', 'loss']),
+        cfg('ConstRate', ['gain', 'loss', 'dupl'], dupl=0.05),
+        cfg('ConstRateDemi', ['gain', 'loss', 'dupl', 'demidupl_gain'], dupl=0.05, demidupl_gain=0.01),
+        cfg('ConstRateDemiEst', ['gain', 'loss', 'dupl', 'demidupl_gain', 'demidupl_loss'],
+            dupl=0.05, demidupl_gain=0.01, demidupl_loss=0.01),
+        cfg('ConstRateNoDupl', ['gain', 'loss', 'demidupl_gain'], demidupl_gain=0.01),
+        cfg('LinearRate', ['gain', 'loss', 'dupl', 'linear_rate'], dupl=0.05, linear_rate=0.01),
+        cfg('LinearRateDemi', ['gain', 'loss', 'dupl', 'demidupl_gain', 'linear_rate'], dupl=0.05,
+            demidupl_gain=0.01, linear_rate=0.01),
+        {'name': 'FullModelDefaultRates', 'initial_params': None,
+         'params_to_optimize': ['gain', 'loss', 'dupl', 'demidupl_gain', 'demidupl_loss',
+                                'base_number_gain', 'base_number_loss', 'linear_rate']},
+    ]
+
+
+def sharded_model_selection(select, model_configurations):
+    """Model-selection candidates are independent optimiser runs (AR:756 loop bodies share only
+    the read-only tree): candidate k runs on rank k % world (round robin, SURVEY.md section 8(d) config
+    4) through `select(configs) -> dict name -> result` (calculate_model_selection_criteria
+    with the tree and counts bound), and every rank receives the merged dict in candidate order."""
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    mine = [c for k, c in enumerate(model_configurations) if k % world == rank]
+    local = select(mine) if mine else {}
+    if world == 1:
+        return local
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    merged = {}
+    for c in model_configurations:
+        for part in gathered:
+            if c['name'] in part:
+                merged[c['name']] = part[c['name']]
+    return merged
+
+
 def sum_across_ranks(tensor):
     """In-place sum (histograms of the simulator); no-op for a single process."""
     if dist.is_initialized() and dist.get_world_size() > 1:

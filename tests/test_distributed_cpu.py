@@ -53,3 +53,39 @@ def test_sharded_evaluation_gathers_on_every_rank(tmp_path, total):
     want = -(rows[:, 0] * 2.0 + rows[:, 7])
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"r{r}.npy"), want)
+
+
+def _selection_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import json
+    from chromevol_enhanced_b200 import distributed as D
+    D.init_from_env(backend="gloo")
+    configs = D.chromevol_model_configurations()
+
+    def fake_select(cfgs):                  # stands in for calculate_model_selection_criteria
+        return {c['name']: {'AIC': 2.0 * len(c['params_to_optimize']), 'rank': rank} for c in cfgs}
+
+    merged = D.sharded_model_selection(fake_select, configs)
+    with open(os.path.join(out_dir, f"sel{rank}.json"), "w") as fh:
+        json.dump(merged, fh)
+    dist.destroy_process_group()
+
+
+def test_model_selection_candidates_are_sharded_round_robin(tmp_path):
+    import json
+    from chromevol_enhanced_b200 import distributed as D
+    world = 2
+    mp.spawn(_selection_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    configs = D.chromevol_model_configurations()
+    names = [c['name'] for c in configs]
+    assert len(names) == len(set(names)) == 8
+    for r in range(world):
+        merged = json.load(open(tmp_path / f"sel{r}.json"))
+        assert list(merged) == names                                 # candidate order, every rank
+        for k, c in enumerate(configs):
+            assert merged[c['name']]['rank'] == k % world
+            assert merged[c['name']]['AIC'] == 2.0 * len(c['params_to_optimize'])
+    # single process: no collective
+    solo = D.sharded_model_selection(lambda cfgs: {c['name']: 1 for c in cfgs}, configs)
+    assert list(solo) == names
