@@ -1012,7 +1012,7 @@ static int launch_apply_fast(ApplyArgs& a, int B, cudaStream_t st) {
     const size_t one_stage = sizeof(double) * (size_t)F_KC * F_JT * 32;
     if (fixed + one_stage > g_f_optin) return 1;  // does not fit: caller tries a smaller variant
     size_t ring = g_f_optin - fixed;
-    size_t ring_max = (NW >= 15 ? F_MAXSTAGE : (NW == 7 ? 2 : 1)) * one_stage;  // narrow CTAs: more per SM
+    size_t ring_max = (NW >= 15 ? F_MAXSTAGE : 1) * one_stage;  // narrow CTAs: more of them per SM
     if (ring > ring_max) ring = ring_max;
     a.stage_doubles_cap = (int)(ring / sizeof(double));
     const size_t smem = fixed + ring;
@@ -1042,7 +1042,7 @@ static int launch_apply_shapes(ApplyArgs& a, int B, cudaStream_t st) {
     // (thresholds measured on B200 with tools/level_probe.py; CEVB_TW / CEVB_TM / CEVB_TS override them)
     int rc = 1;
     const int tw = getenv("CEVB_TW") ? atoi(getenv("CEVB_TW")) : 300;    // wide: 15 consumer warps
-    const int tm = getenv("CEVB_TM") ? atoi(getenv("CEVB_TM")) : 100000; // medium: 7
+    const int tm = getenv("CEVB_TM") ? atoi(getenv("CEVB_TM")) : 100;    // medium: 7
     const int ts = getenv("CEVB_TS") ? atoi(getenv("CEVB_TS")) : 8;      // small: 3, else 1
     if (a.n_items > tw) rc = launch_apply_variant<1, 15, MODE>(a, B, st);
     if (rc == 1 && a.n_items > tm) rc = launch_apply_variant<1, 7, MODE>(a, B, st);
