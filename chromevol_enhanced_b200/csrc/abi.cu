@@ -74,6 +74,22 @@ __global__ void __launch_bounds__(512) dmma_probe_kernel(int iters, int smem_mod
 #pragma unroll
             for (int i = 0; i < 13; ++i) dmma884(c[i][0], c[i][1], av, bp[i * 32]);
         }
+    } else if (smem_mode >= 100) {
+        // 13 DMMAs + (smem_mode - 100) independent DADDs per iteration, register operands: what
+        // FP64 ALU work in the epilogue costs the tensor pipe (about 2.5 clocks per DADD)
+        const int nadd = smem_mode - 100;
+        double e0 = av, e1 = bv, e2 = av + 1.0, e3 = bv + 1.0;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 13; ++i) dmma884(c[i][0], c[i][1], av, bv);
+            for (int q = 0; q < nadd; q += 4) {
+                e0 += av;
+                e1 += av;
+                e2 += av;
+                e3 += av;
+            }
+        }
+        bv = e0 + e1 + e2 + e3;
     } else if (smem_mode == 5) {
         // 13 volatile loads (kept in program order by ptxas) and then the 13 DMMAs
         for (int it = 0; it < iters; ++it) {

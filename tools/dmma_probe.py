@@ -17,7 +17,9 @@ sms = info["sm_count"]
 iters = 4000
 for mode, name in ((0, "registers"), (1, "LDS per DMMA"), (2, "LDS double-buffered"),
                    (3, "13 LDS then 13 DMMA"), (4, "LDS.128 per 2 DMMA"),
-                   (5, "13 volatile LDS, 13 DMMA"), (6, "volatile, 2 register sets")):
+                   (5, "13 volatile LDS, 13 DMMA"), (6, "volatile, 2 register sets"),
+                   (100, "13 DMMA + 0 DADD"), (108, "13 DMMA + 8 DADD"), (128, "13 DMMA + 28 DADD"),
+                   (152, "13 DMMA + 52 DADD")):
     line = []
     for warps in (1, 2, 4, 8, 12, 16):
         lib.cevb_diag_dmma_probe(sms, warps * 32, 50, mode, _lib.ptr(sink), st)
