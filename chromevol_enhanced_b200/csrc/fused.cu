@@ -638,18 +638,19 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
             }
         }
     };
-    // end of a row: quad reduction and the two stores (the combine kernel forms d / r, AR:154)
+    // end of a row: quad reduction and the two stores (the combine kernel forms d / r, AR:154).
+    // The sum over the four lanes of a quad is one DMMA per quantity (partials as the 8x4 A
+    // operand times a matrix of ones) instead of a chain of dependent shuffles: the result is only
+    // read by the stores, so the warp keeps issuing.
     auto finish_row = [&](const int i_e) {
         if (EVAL) return;
-        double r = rs0 + rs1, d = dt0 + dt1;
-        r += __shfl_xor_sync(0xffffffffu, r, 1);
-        d += __shfl_xor_sync(0xffffffffu, d, 1);
-        r += __shfl_xor_sync(0xffffffffu, r, 2);
-        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        double r0 = 0.0, r1 = 0.0, d0 = 0.0, d1 = 0.0;
+        dmma884(r0, r1, rs0 + rs1, 1.0);
+        dmma884(d0, d1, dt0 + dt1, 1.0);
         if (t4 == 0 && mine) {
             const size_t o = ((size_t)b * a.n_nodes + my_child) * a.ldp + i_e;
-            a.w[o] = d;
-            a.wr[o] = r;
+            a.w[o] = d0;
+            a.wr[o] = r0;
         }
         rs0 = rs1 = dt0 = dt1 = 0.0;
     };
