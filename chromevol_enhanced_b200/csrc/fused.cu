@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     // epilogue of one accumulator tile of the item (row i_e, pass pass_e): floor (AR:153), row
     // sum, dot product with L_child -- or the raw store for the squaring kernel
     auto epi_tile = [&](const int jt, double p0, double p1, const int i_e, const int pass_e,
-                        const int njt_e) {
+                        const int njt_e, const bool floored) {
         if (EVAL) {
             const int j = pass_e * F_JT * 8 + jt * 8 + 2 * t4;
             if (mine && jt < njt_e && j < a.ldp)
@@ -604,10 +604,12 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
             // one pass of exactly 13 tiles (97 <= n <= 104): branch-free.  The padding columns
             // of the last tile hold exact zeros (zero coefficients), so a "floor" of 0 removes
             // them from the row sum.
-            const double f0 = (jt == F_JT - 1) ? fl_last0 : 1e-12;
-            const double f1 = (jt == F_JT - 1) ? fl_last1 : 1e-12;
-            p0 = (__double_as_longlong(p0) < floor_bits) ? f0 : p0;
-            p1 = (__double_as_longlong(p1) < floor_bits) ? f1 : p1;
+            if (!floored) {
+                const double f0 = (jt == F_JT - 1) ? fl_last0 : 1e-12;
+                const double f1 = (jt == F_JT - 1) ? fl_last1 : 1e-12;
+                p0 = (__double_as_longlong(p0) < floor_bits) ? f0 : p0;
+                p1 = (__double_as_longlong(p1) < floor_bits) ? f1 : p1;
+            }
             rs0 += p0;
             rs1 += p1;
             if (MODE == APPLY_LEAF) {
@@ -682,11 +684,20 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
                 asm volatile("" ::: "memory");
 #pragma unroll
                 for (int jt = 0; jt < F_JT; ++jt) {
-                    const double p0 = acc[jt][0], p1 = acc[jt][1];
+                    double p0 = acc[jt][0], p1 = acc[jt][1];
+                    if (fast && !EVAL) {
+                        // the floor consumes the old accumulator values, so no register copy is
+                        // needed before the DMMA overwrites the tile (AR:153; padding columns
+                        // hold exact zeros and get a "floor" of 0)
+                        const double f0 = (jt == F_JT - 1) ? fl_last0 : 1e-12;
+                        const double f1 = (jt == F_JT - 1) ? fl_last1 : 1e-12;
+                        p0 = (__double_as_longlong(p0) < floor_bits) ? f0 : p0;
+                        p1 = (__double_as_longlong(p1) < floor_bits) ? f1 : p1;
+                    }
                     acc[jt][0] = 0.0;
                     acc[jt][1] = 0.0;
                     dmma884(acc[jt][0], acc[jt][1], av, bv[jt]);
-                    if (have_prev) epi_tile(jt, p0, p1, i_prev, pass_prev, njt_prev);
+                    if (have_prev) epi_tile(jt, p0, p1, i_prev, pass_prev, njt_prev, true);
                 }
                 asm volatile("" ::: "memory");
             }
@@ -716,7 +727,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     }
     if (have_prev) {
 #pragma unroll
-        for (int jt = 0; jt < F_JT; ++jt) epi_tile(jt, acc[jt][0], acc[jt][1], i_prev, pass_prev, njt_prev);
+        for (int jt = 0; jt < F_JT; ++jt) epi_tile(jt, acc[jt][0], acc[jt][1], i_prev, pass_prev, njt_prev, false);
         finish_row(i_prev);
     }
 }
