@@ -361,7 +361,12 @@ class LikelihoodEngine:
         applies = int(self.flat.leaf_child.size > 0) + \
             int(np.count_nonzero(np.diff(self.flat.level_child_off)))
         base = (6 if self.squaring == "series" else 11) + (1 if self.want_node_vectors else 0)
-        return base + levels + applies
+        per_slice = base + levels + applies
+        # a chunk of at least 2 * n_streams vectors is issued as n_streams slices, each with its
+        # own launch sequence
+        nb = min(getattr(self, "last_batch", self.chunk), self.chunk)
+        slices = self.n_streams if (self.squaring == "series" and nb >= 2 * self.n_streams) else 1
+        return per_slice * slices
 
     # ------------------------------------------------------------------ public
     def log_likelihood(self, params, root_freq=None, check_growth=True):
