@@ -232,6 +232,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     t_res = D.max_across_ranks(ev0.elapsed_time(ev1) * 1e-3, dev)
     n_chunks = eng.n_chunks
+    launches_per_step = n_chunks * eng.launches_per_chunk()      # of our kernels, all stream slices
     # Pade orders / squaring counts the device chose, from one extra untimed step (deterministic)
     eng.keep_info, eng.info_log = True, []
     step_resident()
@@ -357,7 +358,7 @@ def run_ours(args):
         "config": workload_config(args, world),
         "e2e": {"value": total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 9 * 8),
                 "d2h_bytes_per_step": int(B * 8), "ms_per_step": t_e2e / args.steps * 1e3},
-        "gpu_launches": int(args.steps * n_chunks * eng.launches_per_chunk()),
+        "gpu_launches": int(args.steps * launches_per_step),
         "roofline": {"kernel": "taylor_apply_kernel", "bound": "tensor", "achieved": apply_tf,
                      "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": (apply_tf / fp64_peak) if apply_tf else None,
