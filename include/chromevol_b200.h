@@ -45,7 +45,7 @@ extern "C" {
 #define CEVB_MAX_SPARSE 12
 #define CEVB_NEVENT 8
 #define CEVB_MAX_N 288           /* largest supported matrix order (states 0..287) */
-#define CEVB_TAYLOR_KC 10       /* chunks of 4 series coefficients kept per vector: degrees 0..39 */
+#define CEVB_TAYLOR_KC 12       /* chunks of 4 series coefficients kept per vector: degrees 0..47 */
 #define CEVB_TAYLOR_TRUNC 1e-17 /* truncation bound of the series: a tenth of the unit roundoff  */
 #define CEVB_FUSED_INIT 1
 #define CEVB_FUSED_APPLY 2
@@ -124,8 +124,8 @@ int cevb_expm_branches_list(const double* pw, const double* norms, const uint16_
  *   doubles per vector); chunk c of row i holds degrees 4c..4c+3 interleaved per column.
  * The number of terms for a pair is the smallest K + 1 with
  *     x^(K+1)/(K+1)! / (1 - x/(K+2)) e^{-mu t} <= CEVB_TAYLOR_TRUNC,  x = nu t;
- * cevb_expm_plan lists every (vector, branch length) pair for which 40 terms do not reach
- * that (nu t above about 7), which needs scaling and squaring and therefore a materialised
+ * cevb_expm_plan lists every (vector, branch length) pair for which 4 * CEVB_TAYLOR_KC = 48 terms do not
+ * reach that (nu t above about 9.5), which needs scaling and squaring and therefore a materialised
  * matrix: slot [B][E] = position in worklist (-1 = fused path, -2 = list overflow),
  * work_s [cap] = squarings of that position (may be NULL), *count = pairs found (may exceed
  * cap; the caller then re-plans).  It also records the decision per pair for the kernels:
