@@ -5,7 +5,7 @@ from __future__ import annotations
 import numpy as np
 
 KC = 12              # CEVB_TAYLOR_KC
-TRUNC = 1e-17        # CEVB_TAYLOR_TRUNC
+TRUNC = 1e-18        # CEVB_TAYLOR_TRUNC
 
 
 def taylor_ncoef(x, mut):

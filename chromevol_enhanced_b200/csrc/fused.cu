@@ -37,7 +37,7 @@ constexpr double F_TRUNC = CEVB_TAYLOR_TRUNC;  // truncation bound of the series
 // For a generator Q + mu I is entrywise non-negative, so the sum has no cancellation and its
 // norm nu = min(||Q + mu I||_1, ||Q + mu I||_inf) is about half of ||Q||_1.
 // Number of series coefficients (degree + 1) so that the truncation bound
-//     x^(K+1)/(K+1)! / (1 - x/(K+2)) * e^{-mu t} <= 1e-17 (a tenth of the unit roundoff),   x = nu t;
+//     x^(K+1)/(K+1)! / (1 - x/(K+2)) * e^{-mu t} <= 1e-18 (CEVB_TAYLOR_TRUNC),   x = nu t;
 // a result above 4 * F_KC means the coefficient table is too short (scale and square).
 __host__ __device__ inline int taylor_ncoef(double x, double mut) {
     if (!(x > 0.0)) return 1;

@@ -46,7 +46,11 @@ extern "C" {
 #define CEVB_NEVENT 8
 #define CEVB_MAX_N 288           /* largest supported matrix order (states 0..287) */
 #define CEVB_TAYLOR_KC 12       /* chunks of 4 series coefficients kept per vector: degrees 0..47 */
-#define CEVB_TAYLOR_TRUNC 1e-17 /* truncation bound of the series: a tenth of the unit roundoff  */
+#define CEVB_TAYLOR_TRUNC 1e-18 /* absolute truncation bound of the series.  Two orders below the
+                                   unit roundoff on purpose: likelihoods of improbable data are
+                                   sums of entries near the 1e-12 floor, and logL parity at 1e-9
+                                   relative there needs ~1e-21 .. 1e-18 absolute on those entries
+                                   (1e-16 fails tests/test_gpu_random.py, 1e-17 passes by 1x) */
 #define CEVB_FUSED_INIT 1
 #define CEVB_FUSED_APPLY 2
 #define CEVB_FUSED_COMBINE 4
