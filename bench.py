@@ -472,6 +472,12 @@ def main():
                     help="also time the stochastic mapper (configs[4]) and an N=256 / 10,000-taxon "
                          "evaluation (configs[3]); adds about a minute")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that print to file descriptor 1 (NCCL's
+    # version banner on rank 0) are sent to stderr, and the JSON line goes to the real stdout
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)
