@@ -43,14 +43,17 @@ for r in range(reps):
         acc[key] += a.elapsed_time(b) / reps
 sizes = [int(flat.leaf_child.size)] + np.diff(flat.level_child_off).tolist()
 tot = {}
-line = []
+apply_ms = [0.0] * len(sizes)          # a batch larger than one chunk repeats the launch sequence
+combine_ms = [0.0] * flat.n_levels
 for key in order:
     tot[key[0]] = tot.get(key[0], 0.0) + acc[key]
     if key[0] == "apply":
-        line.append(f"{sizes[key[1]]}:{acc[key]:.2f}")
-print("apply per launch (items:ms):", " ".join(line))
-print("combine per level (nodes:ms):", " ".join(f"{c}:{acc[k]:.3f}" for c, k in zip(
-    np.diff(flat.level_off).tolist(), [k for k in order if k[0] == "combine"])))
+        apply_ms[key[1] % len(sizes)] += acc[key]
+    elif key[0] == "combine":
+        combine_ms[key[1] % flat.n_levels] += acc[key]
+print("apply per launch (items:ms):", " ".join(f"{c}:{t:.2f}" for c, t in zip(sizes, apply_ms)))
+print("combine per level (nodes:ms):", " ".join(f"{c}:{t:.3f}" for c, t in zip(
+    np.diff(flat.level_off).tolist(), combine_ms)))
 print("totals ms:", {k: round(v, 2) for k, v in tot.items()})
 # un-instrumented wall time
 torch.cuda.synchronize()
