@@ -1,11 +1,12 @@
 import sys, os, ctypes
-sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "..")))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np, torch
 from chromevol_enhanced_b200 import synthetic, _lib
 from chromevol_enhanced_b200.engine import ExpmWorkspace, _stream_ptr
 from oracle import chromevol_oracle as O
 from oracle.expm_amh import expm_amh
-from tools.device_model import prepare, select, expm_model, postprocess
+from device_model import prepare, select, expm_model, postprocess
 np.set_printoptions(linewidth=200, precision=4)
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 35
 n = N + 1
