@@ -505,13 +505,16 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // child vectors (one-hot / uniform / conditional-likelihood vector of an internal child).
-    // Eight independent loads per thread are in flight before the first store: a load-store loop
-    // per element serialised ~25 HBM latencies per warp, 8-10 % of a level CTA's lifetime.
-    if (!LEAF) {
+    __syncthreads();   // barriers initialised
+
+    if (warp != NW && !LEAF) {
+        // child vectors (one-hot / uniform / conditional-likelihood vector of an internal child),
+        // staged by the consumer warps while the producer already fills the ring.  Eight
+        // independent loads per thread are in flight before the first store: a load-store loop
+        // per element serialised ~25 HBM latencies per warp, 8-10 % of a level CTA's lifetime.
         const double unif = 1.0 / (double)n;  // AR:211
         const int total = EB * ldl;
-        constexpr int NT = 32 * (NW + 1);
+        constexpr int NT = 32 * NW;
         for (int q0 = tid; q0 < total; q0 += NT * 8) {
             double v[8];
 #pragma unroll
@@ -533,8 +536,8 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
                 if (q < total) Ls[q] = v[u];
             }
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NW) : "memory");   // consumer warps only
     }
-    __syncthreads();
 
     if (warp == NW) {
         // ---- producer: one lane streams the (row, pass) tiles of the coefficient table.  Rows
