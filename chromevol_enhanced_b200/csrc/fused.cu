@@ -903,24 +903,21 @@ __global__ void __launch_bounds__(128) combine_level_warp_kernel(
     int nres = 0;
     const double unif = 1.0 / (double)n;
     const int c_begin = child_off[node], c_end = child_off[node + 1];
-    for (int ci = c_begin; ci < c_end; ++ci) {
-        const int child = child_idx[ci];
-        const int code = leaf_code[child];
-        int md = mode[(size_t)b * n_nodes + child];
+    // one child: v *= P_child @ L_child and the AR:241 rescale; (wp, rp) are this child's rows of
+    // w / wr, loaded by the caller for two children at a time so that their latencies overlap
+    auto apply_child = [&](const int child, const int code, int md, const double (&wp)[4],
+                           const double (&rp)[4]) {
         const double* cv = node_vec + ((size_t)b * n_nodes + child) * ldp;
         double x[4];
         if (md == 0) {
-            const double* wv = w + ((size_t)b * n_nodes + child) * ldp;
-            const double* rv = wr + ((size_t)b * n_nodes + child) * ldp;
             int bad = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int i = lane + 32 * k;
                 x[k] = 1.0;
                 if (i < n) {
-                    const double r = rv[i];
-                    bad |= !(fabs(r) < INFINITY);   // NaN / inf in P -> identity (AR:156-159)
-                    x[k] = wv[i] / r;
+                    bad |= !(fabs(rp[k]) < INFINITY);   // NaN / inf in P -> identity (AR:156-159)
+                    x[k] = wp[k] / rp[k];
                 }
             }
             if (__any_sync(0xffffffffu, bad)) md = 1;
@@ -985,6 +982,29 @@ __global__ void __launch_bounds__(128) combine_level_warp_kernel(
             for (int k = 0; k < 4; ++k) v[k] = v[k] / s;
             ++nres;
         }
+    };
+    for (int ci = c_begin; ci < c_end; ci += 2) {
+        const bool two = ci + 1 < c_end;
+        const int child0 = child_idx[ci], child1 = two ? child_idx[ci + 1] : child0;
+        const int code0 = leaf_code[child0], code1 = leaf_code[child1];
+        const int md0 = mode[(size_t)b * n_nodes + child0], md1 = mode[(size_t)b * n_nodes + child1];
+        // rows of w / wr exist for every node; they are only used where mode == 0
+        const double* w0 = w + ((size_t)b * n_nodes + child0) * ldp;
+        const double* r0 = wr + ((size_t)b * n_nodes + child0) * ldp;
+        const double* w1 = w + ((size_t)b * n_nodes + child1) * ldp;
+        const double* r1 = wr + ((size_t)b * n_nodes + child1) * ldp;
+        double wp0[4], rp0[4], wp1[4], rp1[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = lane + 32 * k;
+            const bool in = i < n;
+            wp0[k] = in ? w0[i] : 1.0;      // not predicated on mode: the loads must not wait for it
+            rp0[k] = in ? r0[i] : 1.0;
+            wp1[k] = in ? w1[i] : 1.0;
+            rp1[k] = in ? r1[i] : 1.0;
+        }
+        apply_child(child0, code0, md0, wp0, rp0);
+        if (two) apply_child(child1, code1, md1, wp1, rp1);
     }
     double* out = node_vec + ((size_t)b * n_nodes + node) * ldp;
 #pragma unroll
@@ -1411,7 +1431,7 @@ extern "C" int cevb_prune_fused(const double* tc, const double* norms, const dou
         // wide levels: one warp per (node, vector) -- a quarter of the CTAs and no block
         // barriers; narrow levels keep the block kernel, whose four warps share the (rare but
         // long) mat-vec of a materialised P
-        if ((stages & CEVB_FUSED_COMBINE) && n <= 128 && cnt >= 100) {
+        if ((stages & CEVB_FUSED_COMBINE) && n <= 128 && cnt >= 30) {
             const long long tasks = (long long)cnt * B;
             combine_level_warp_kernel<<<(unsigned)((tasks + 3) / 4), 128, 0, st>>>(
                 w, wr, mode, P, slot, E, n, ldp, n_nodes, root, cnt, B,
