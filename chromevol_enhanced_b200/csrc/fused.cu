@@ -213,15 +213,19 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
             }
         }
     }
-    for (int x = tid; x < TCR * npad; x += 128) {
-        const int r = x / npad, j = x - r * npad;
-        cur[x] = (j == i0 + r) ? 1.0 : 0.0;
+    for (int j = tid; j < npad; j += 128) {
+#pragma unroll
+        for (int r = 0; r < TCR; ++r) cur[r * npad + j] = (j == i0 + r) ? 1.0 : 0.0;
     }
+    // the longest sparse column among this warp's threads bounds the unrolled product below
+    // (typically 6-8 of the 12 slots are in use)
+    const int cmax = __reduce_max_sync(0xffffffffu, (j0 < n && cnt0 != 255) ? cnt0 : 0);
     __syncthreads();
     for (int k = 0; k < k_end; ++k) {
-        for (int x = tid; x < TCR * npad; x += 128) {
-            const int r = x / npad, j = x - r * npad;
-            stg[(size_t)(r * npad + j) * 4 + (k & 3)] = (j < n) ? cur[x] : 0.0;
+        for (int j = tid; j < npad; j += 128) {
+#pragma unroll
+            for (int r = 0; r < TCR; ++r)
+                stg[(size_t)(r * npad + j) * 4 + (k & 3)] = (j < n) ? cur[r * npad + j] : 0.0;
         }
         if (k + 1 < k_end) {
             const double inv = 1.0 / (double)(k + 1);
@@ -238,8 +242,11 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
                 } else {
 #pragma unroll
                     for (int q = 0; q < CEVB_MAX_SPARSE; ++q) {
+                        if (q < cmax) {   // warp-uniform
 #pragma unroll
-                        for (int r = 0; r < TCR; ++r) acc[r] = fma(cur[r * npad + ridx[q]], qval[q], acc[r]);
+                            for (int r = 0; r < TCR; ++r)
+                                acc[r] = fma(cur[r * npad + ridx[q]], qval[q], acc[r]);
+                        }
                     }
                 }
 #pragma unroll
@@ -265,9 +272,10 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
         if ((k & 3) == 3) {
             for (int r = 0; r < TCR; ++r) {
                 if (i0 + r >= n) break;
-                double* dst = tc + (((size_t)b * n + i0 + r) * F_KC + (k >> 2)) * npad * 4;
-                const double* src = stg + (size_t)r * npad * 4;
-                for (int x = tid; x < npad * 4; x += 128) dst[x] = src[x];
+                double2* dst = reinterpret_cast<double2*>(
+                    tc + (((size_t)b * n + i0 + r) * F_KC + (k >> 2)) * npad * 4);
+                const double2* src = reinterpret_cast<const double2*>(stg + (size_t)r * npad * 4);
+                for (int x = tid; x < npad * 2; x += 128) dst[x] = src[x];
             }
             __syncthreads();
         }
