@@ -60,6 +60,10 @@ _PROTOTYPES = {
     "cevb_stoch_map": (_c.c_int, [c_dp, _c.c_int, c_dp, _c.c_int, c_dp, c_dp, c_dp, _c.c_int,
                                   _c.c_ulonglong, _c.c_longlong, _c.c_longlong, _c.c_int, c_dp, c_dp,
                                   c_dp, _c.c_longlong, c_dp, _c.c_void_p]),
+    "cevb_stoch_map_sets": (_c.c_int, [c_dp, _c.c_int, _c.c_longlong, c_dp, c_dp, _c.c_int, c_dp,
+                                       _c.c_int, c_dp, c_dp, c_dp, _c.c_ulonglong, _c.c_longlong,
+                                       _c.c_longlong, _c.c_int, c_dp, c_dp, c_dp, _c.c_longlong,
+                                       c_dp, _c.c_void_p]),
     "cevb_stoch_branch_trace": (_c.c_int, [c_dp, _c.c_int, _c.c_int, _c.c_double, _c.c_int,
                                            _c.c_ulonglong, _c.c_ulonglong, _c.c_int, c_dp, c_dp, c_dp,
                                            c_dp, c_dp, _c.c_void_p]),

@@ -16,7 +16,8 @@ import scipy.optimize as opt
 import torch
 
 from . import _lib
-from .engine import (LikelihoodEngine, params_to_row, rate_matrix, transition_matrices)
+from .engine import (LikelihoodEngine, branch_parameter_sets, params_to_row, rate_matrix,
+                     transition_matrices)
 from .flatten import FlatTree
 
 # AR:22
@@ -97,6 +98,8 @@ class ChromEvolLikelihoodCalculator:
         self._flat = None
         self._flat_key = None
         self._engine = None
+        self._het_engine = None      # materialised-path engine for branch-specific parameter sets
+        self._het_key = None
         self._last_logl = None
 
     # -- device state ---------------------------------------------------------------------
@@ -104,6 +107,7 @@ class ChromEvolLikelihoodCalculator:
         """Drop the cached flattened tree (call after editing the tree or the counts dict)."""
         self._flat = None
         self._engine = None
+        self._het_engine = None
         self.likelihoods = {}
 
     def _device_engine(self):
@@ -131,18 +135,36 @@ class ChromEvolLikelihoodCalculator:
 
     def _up_pass(self):
         """One device evaluation; fills ``likelihoods`` (id(node) -> ndarray) like the memo dict."""
-        if self._has_branch_params():
-            raise NotImplementedError(
-                "branch-specific parameters (set_branch_parameters) are not on the device path "
-                "yet (SURVEY.md section 8 row f4)")
         if self.root_frequencies is None:
             self.set_root_frequencies(None)
+        if self._has_branch_params():
+            return self._up_pass_branch_sets()
         eng = self._device_engine()
         logl = eng.log_likelihood(params_to_row(self.model.params)[None, :],
                                   root_freq=self.root_frequencies)
         vec = eng.node_vectors(0).cpu().numpy()
         self.likelihoods = {id(nd): vec[k] for k, nd in enumerate(self._flat.nodes)}
         self._last_logl = float(logl[0].item())
+        return self._last_logl
+
+    def branch_parameter_sets(self):
+        """(rows (S, 9), node_set (n_nodes,)) of a branch-heterogeneous model; set 0 = model.params."""
+        self._device_engine()
+        return branch_parameter_sets(self.model, self._flat)
+
+    def _up_pass_branch_sets(self):
+        """Branch-specific parameters (set_branch_parameters, AR:67-73): every distinct set's
+        matrices on the device, one pruning pass over the per-branch selection."""
+        self._device_engine()
+        if self._het_engine is None or self._het_key != self._flat_key:
+            self._het_engine = LikelihoodEngine(self._flat, path="materialised")
+            self._het_key = self._flat_key
+        rows, node_set = self.branch_parameter_sets()
+        eng = self._het_engine
+        logl = eng.log_likelihood_branch_sets(rows, node_set, root_freq=self.root_frequencies)
+        vec = eng.node_vectors(0).cpu().numpy()
+        self.likelihoods = {id(nd): vec[k] for k, nd in enumerate(self._flat.nodes)}
+        self._last_logl = float(logl.item())
         return self._last_logl
 
     def calculate_likelihood_at_node(self, node):
@@ -176,6 +198,9 @@ class ChromEvolLikelihoodCalculator:
         order = {nm: k for k, nm in enumerate(MODEL_PARAMETER_NAMES + ['base_number'])}
         for j, nm in enumerate(names):
             rows[:, order[nm]] = X[:, j]
+        if self._has_branch_params():
+            raise NotImplementedError("log_likelihood_batch varies the model-wide parameters; "
+                                      "branch-specific sets are evaluated one model at a time")
         eng = self._device_engine()
         return eng.log_likelihood(rows, root_freq=self.root_frequencies).cpu().numpy()
 
@@ -189,6 +214,8 @@ class ChromEvolLikelihoodCalculator:
         # somewhere else
         if any(id(nd) not in self.likelihoods for nd in flat.nodes):
             self._up_pass()
+        if self._has_branch_params():
+            eng = self._het_engine        # the engine that holds the vectors of the last up-pass
         ml_count, ml_prob, probs = eng.ancestral_states(0, want_probs=True)
         ml_count = ml_count.cpu().numpy()
         ml_prob = ml_prob.cpu().numpy()

@@ -133,10 +133,14 @@ __global__ void __launch_bounds__(MT) stoch_map_kernel(
     const int32_t* __restrict__ parent, const int32_t* __restrict__ preorder,
     const double* __restrict__ branch_len, int bn, unsigned long long seed, long long rep0,
     long long count, int n_bins, uint32_t* __restrict__ hist, unsigned long long* __restrict__ sums,
-    uint16_t* __restrict__ state, long long stride, unsigned long long* __restrict__ n_events) {
+    uint16_t* __restrict__ state, long long stride, unsigned long long* __restrict__ n_events,
+    int n_sets, long long q_stride, const int32_t* __restrict__ node_set,
+    const int32_t* __restrict__ bn_set, unsigned int tbytes) {
+    // one compact table per parameter set (branch-specific models, AR:569: the branch above a
+    // node uses branch_params.get(id(node), params)); n_sets == 1 is the homogeneous model
     extern __shared__ __align__(16) unsigned char raw[];
-    const QTable tb = carve_table(raw, n);
-    build_table(tb, q, n, ldq);
+    for (int qs = 0; qs < n_sets; ++qs)
+        build_table(carve_table(raw + (size_t)qs * tbytes, n), q + (size_t)qs * q_stride, n, ldq);
 
     const long long slot = (long long)blockIdx.x * MT + threadIdx.x;
     const bool active = slot < count;
@@ -166,6 +170,10 @@ __global__ void __launch_bounds__(MT) stoch_map_kernel(
     for (int k = 1; k < n_nodes; ++k) {
         const int node = preorder[k];
         const double t = branch_len[node];
+        const int qs = node_set ? node_set[node] : 0;
+        const QTable tb = carve_table(raw + (size_t)qs * tbytes, n);
+        const double* qn = q + (size_t)qs * q_stride;
+        const int bnn = bn_set ? bn_set[qs] : bn;
         int s = state[(size_t)parent[node] * stride + sl];
         int c[CEVB_NEVENT];
 #pragma unroll
@@ -182,8 +190,8 @@ __global__ void __launch_bounds__(MT) stoch_map_kernel(
                 if (time + dt >= t) break;                             // AR:491-493
                 time += dt;
                 if (tb.tot[s] <= 1e-9) break;                          // AR:505-507
-                const int nxt = pick_next(tb, q, n, ldq, s, u1);
-                const int ty = classify_event(s, nxt, bn);
+                const int nxt = pick_next(tb, qn, n, ldq, s, u1);
+                const int ty = classify_event(s, nxt, bnn);
 #pragma unroll
                 for (int e = 0; e < CEVB_NEVENT; ++e) c[e] += (e == ty);
                 s = nxt;
@@ -256,19 +264,30 @@ __global__ void stoch_branch_trace_kernel(const double* __restrict__ q, int n, i
 
 using namespace cevb;
 
-extern "C" int cevb_stoch_map(const double* q, int n, const double* root_probs, int n_nodes,
-                              const int32_t* parent, const int32_t* preorder,
-                              const double* branch_len, int base_number, unsigned long long seed,
-                              long long rep_begin, long long rep_end, int n_bins, uint32_t* hist,
-                              unsigned long long* sums, uint16_t* state_scratch, long long rep_chunk,
-                              unsigned long long* n_events, void* stream) {
+static int stoch_map_impl(const double* q, int n_sets, long long q_stride, const int32_t* node_set,
+                          const int32_t* bn_set, int n, const double* root_probs, int n_nodes,
+                          const int32_t* parent, const int32_t* preorder, const double* branch_len,
+                          int base_number, unsigned long long seed, long long rep_begin,
+                          long long rep_end, int n_bins, uint32_t* hist, unsigned long long* sums,
+                          uint16_t* state_scratch, long long rep_chunk, unsigned long long* n_events,
+                          void* stream) {
     if (rep_end <= rep_begin) return 0;
-    if (n < 2 || n > 65535 || n_bins < 2 || rep_chunk < 1) {
-        set_error("cevb_stoch_map: bad arguments (n=%d, n_bins=%d, rep_chunk=%lld)", n, n_bins, rep_chunk);
+    if (n < 2 || n > 65535 || n_bins < 2 || rep_chunk < 1 || n_sets < 1) {
+        set_error("cevb_stoch_map: bad arguments (n=%d, n_bins=%d, rep_chunk=%lld, n_sets=%d)", n,
+                  n_bins, rep_chunk, n_sets);
         return -1;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = table_bytes(n);
+    const size_t tbytes = (table_bytes(n) + 15) / 16 * 16;
+    const size_t smem = tbytes * (size_t)n_sets;
+    int dev = 0, optin = 0;
+    CEVB_CHECK_CUDA(cudaGetDevice(&dev));
+    CEVB_CHECK_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem > (size_t)optin) {
+        set_error("cevb_stoch_map: %d parameter sets of order %d need %zu B of shared memory", n_sets,
+                  n, smem);
+        return -1;
+    }
     CEVB_CHECK_CUDA(cudaFuncSetAttribute(stoch_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
     for (long long r0 = rep_begin; r0 < rep_end; r0 += rep_chunk) {
@@ -276,10 +295,39 @@ extern "C" int cevb_stoch_map(const double* q, int n, const double* root_probs, 
         const long long blocks = (count + MT - 1) / MT;
         stoch_map_kernel<<<(unsigned)blocks, MT, smem, st>>>(
             q, n, ldq_of(n), root_probs, n_nodes, parent, preorder, branch_len, base_number, seed, r0,
-            count, n_bins, hist, sums, state_scratch, rep_chunk, n_events);
+            count, n_bins, hist, sums, state_scratch, rep_chunk, n_events, n_sets, q_stride, node_set,
+            bn_set, (unsigned int)tbytes);
         CEVB_CHECK_LAUNCH("stoch_map_kernel");
     }
     return 0;
+}
+
+extern "C" int cevb_stoch_map(const double* q, int n, const double* root_probs, int n_nodes,
+                              const int32_t* parent, const int32_t* preorder,
+                              const double* branch_len, int base_number, unsigned long long seed,
+                              long long rep_begin, long long rep_end, int n_bins, uint32_t* hist,
+                              unsigned long long* sums, uint16_t* state_scratch, long long rep_chunk,
+                              unsigned long long* n_events, void* stream) {
+    return stoch_map_impl(q, 1, 0, nullptr, nullptr, n, root_probs, n_nodes, parent, preorder,
+                          branch_len, base_number, seed, rep_begin, rep_end, n_bins, hist, sums,
+                          state_scratch, rep_chunk, n_events, stream);
+}
+
+extern "C" int cevb_stoch_map_sets(const double* q, int n_sets, long long q_stride,
+                                   const int32_t* node_set, const int32_t* base_numbers, int n,
+                                   const double* root_probs, int n_nodes, const int32_t* parent,
+                                   const int32_t* preorder, const double* branch_len,
+                                   unsigned long long seed, long long rep_begin, long long rep_end,
+                                   int n_bins, uint32_t* hist, unsigned long long* sums,
+                                   uint16_t* state_scratch, long long rep_chunk,
+                                   unsigned long long* n_events, void* stream) {
+    if (node_set == nullptr || base_numbers == nullptr) {
+        set_error("cevb_stoch_map_sets: node_set and base_numbers are required");
+        return -1;
+    }
+    return stoch_map_impl(q, n_sets, q_stride, node_set, base_numbers, n, root_probs, n_nodes, parent,
+                          preorder, branch_len, 0, seed, rep_begin, rep_end, n_bins, hist, sums,
+                          state_scratch, rep_chunk, n_events, stream);
 }
 
 extern "C" int cevb_stoch_branch_trace(const double* q, int n, int start_state, double t,

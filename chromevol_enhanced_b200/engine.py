@@ -43,6 +43,26 @@ def params_to_row(params):
     return row
 
 
+def branch_parameter_sets(model, flat):
+    """Distinct parameter sets of a branch-heterogeneous model as (S, 9) rows and, per flattened
+    node, the set used on the branch above it: ``branch_params.get(id(node), params)``
+    (reference AR:230-233 and AR:569).  Set 0 is always ``model.params``."""
+    rows = [params_to_row(model.params)]
+    index = {rows[0].tobytes(): 0}
+    node_set = np.zeros(flat.n_nodes, dtype=np.int64)
+    for k, nd in enumerate(flat.nodes):
+        bp = model.branch_params.get(id(nd))
+        if bp is None:
+            continue
+        row = params_to_row(bp)
+        key = row.tobytes()
+        if key not in index:
+            index[key] = len(rows)
+            rows.append(row)
+        node_set[k] = index[key]
+    return np.stack(rows), node_set
+
+
 def _stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -465,6 +485,54 @@ class LikelihoodEngine:
         self.n_chunks = 1
         self.last_batch = B
         return self._logl[:B].clone()
+
+    def log_likelihood_branch_sets(self, param_rows, node_set, root_freq=None):
+        """Branch-heterogeneous model (reference AR:230-233, where the branch
+        above a child uses ``model.branch_params.get(id(child), model.params)``).
+
+        param_rows: (S, 9) distinct parameter sets; node_set[k]: the set used on the branch above
+        node k (the root's entry is ignored).  Every set's transition matrices are formed for
+        every branch length (S x n_t matrices, the scipy-algorithm kernels), the matrix of each
+        (set, length) pair in use is gathered, and ONE pruning pass runs over the gathered
+        matrices.  Materialised path only.  Returns the log-likelihood as a 0-d CUDA tensor;
+        node vectors / ancestral states of the evaluation are read with which=0."""
+        if self.path != "materialised":
+            raise _lib.CevbError("branch-specific parameter sets need path='materialised'")
+        f = self.flat
+        rows = np.ascontiguousarray(np.atleast_2d(param_rows), dtype=np.float64)
+        S = rows.shape[0]
+        node_set = np.asarray(node_set, dtype=np.int64)
+        if node_set.shape != (f.n_nodes,) or node_set.min() < 0 or node_set.max() >= S:
+            raise ValueError("node_set must hold one parameter-set index per node")
+        d_root = root_freq if torch.is_tensor(root_freq) else self.root_freq_tensor(root_freq)
+        self._ensure(S)
+        ws = self._ws
+        ws.params[:S].copy_(torch.as_tensor(rows, device=self.device))
+        non_root = np.arange(f.n_nodes) != f.root
+        pair = node_set * f.n_t + f.branch_of.astype(np.int64)       # (set, branch-length) index
+        uniq, inverse = np.unique(pair[non_root], return_inverse=True)
+        branch_of = np.zeros(f.n_nodes, dtype=np.int32)
+        branch_of[non_root] = inverse.astype(np.int32)
+        d_branch_of = torch.as_tensor(branch_of, device=self.device)
+        d_uniq = torch.as_tensor(uniq, device=self.device)
+        full_pivot = 0
+        while True:
+            self._transition_matrices(ws, S, full_pivot)
+            if full_pivot or not bool((((ws.info[:S] >> 16) & INFO_GROWTH) != 0).any().item()):
+                break
+            self.repivot_events += 1     # element-growth monitor tripped: full pivoting
+            full_pivot = 1
+        P_het = ws.P[:S].reshape(S * f.n_t, self.n, self.ldp).index_select(0, d_uniq).contiguous()
+        _lib.check(self.lib.cevb_prune(
+            _lib.ptr(P_het), 1, int(uniq.size), self.n, f.n_nodes, f.root,
+            _lib.ptr(self.d_level_nodes),
+            self.h_level_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), f.n_levels,
+            _lib.ptr(self.d_child_off), _lib.ptr(self.d_child_idx), _lib.ptr(d_branch_of),
+            _lib.ptr(self.d_leaf_code), _lib.ptr(d_root), _lib.ptr(self._node_vec),
+            _lib.ptr(self._logl), _lib.ptr(self._rescales), _stream_ptr()), "cevb_prune")
+        self.rescale_counts = self._rescales[:1].clone()
+        self.last_batch = 1
+        return self._logl[0].clone()
 
     def node_vectors(self, which=0):
         """Conditional-likelihood vectors (n_nodes, n) of vector `which` of the last chunk."""

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import params_to_row, _stream_ptr
+from .engine import branch_parameter_sets, params_to_row, _stream_ptr
 from .flatten import FlatTree
 
 EVENT_TYPES = ['gain', 'loss', 'duplication', 'base_number_gain', 'base_number_loss',
@@ -72,11 +72,16 @@ class MappingResult:
 
 def simulate(flat: FlatTree, q_row_params, n, root_probs, n_reps, seed, base_number=0,
              rep_begin=0, rep_end=None, n_bins=256, rep_chunk=1 << 17, device=None, q_matrix=None,
-             return_device=False):
+             return_device=False, node_set=None):
     """Run replicates [rep_begin, rep_end) of an `n_reps`-replicate mapping on the current GPU.
 
     Returns a MappingResult (host arrays), or the raw device tensors when ``return_device``.
+    Branch-specific models: ``q_row_params`` is (S, 9) and ``node_set`` (n_nodes,) names the set
+    of the branch above each node (AR:569); base numbers are taken from the rows.
     """
+    if node_set is not None:
+        return _simulate_sets(flat, q_row_params, node_set, n, root_probs, n_reps, seed, rep_begin,
+                              rep_end, n_bins, rep_chunk, device, return_device)
     _lib.require_device()
     lib = _lib.load()
     device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -111,6 +116,42 @@ def simulate(flat: FlatTree, q_row_params, n, root_probs, n_reps, seed, base_num
     return finalize(flat, hist, sums, n_events, n_reps, n_bins)
 
 
+def _simulate_sets(flat, rows, node_set, n, root_probs, n_reps, seed, rep_begin, rep_end, n_bins,
+                   rep_chunk, device, return_device):
+    _lib.require_device()
+    lib = _lib.load()
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    rep_end = n_reps if rep_end is None else rep_end
+    rows = np.ascontiguousarray(np.atleast_2d(rows), dtype=np.float64)
+    S = rows.shape[0]
+    ldq = lib.cevb_ldq(n)
+    st = _stream_ptr()
+    pw = torch.zeros((S, 7, n, ldq), dtype=torch.float64, device=device)
+    d_params = torch.as_tensor(rows, device=device)
+    _lib.check(lib.cevb_build_q(_lib.ptr(d_params), S, n, _lib.ptr(pw), st), "cevb_build_q")
+    i32 = dict(dtype=torch.int32, device=device)
+    d_set = torch.as_tensor(np.asarray(node_set, dtype=np.int32), **i32)
+    d_bn = torch.as_tensor(rows[:, 8].astype(np.int32), **i32)
+    d_root = torch.as_tensor(np.ascontiguousarray(root_probs, dtype=np.float64), device=device)
+    d_parent = torch.as_tensor(flat.parent, **i32)
+    d_pre = torch.as_tensor(flat.preorder, **i32)
+    d_len = torch.as_tensor(flat.dist_raw, dtype=torch.float64, device=device)
+    hist = torch.zeros((flat.n_nodes, 8, n_bins), dtype=torch.int32, device=device)
+    sums = torch.zeros((flat.n_nodes, 8, 2), dtype=torch.int64, device=device)
+    n_events = torch.zeros(1, dtype=torch.int64, device=device)
+    count = max(0, rep_end - rep_begin)
+    chunk = (int(min(rep_chunk, max(count, 1))) + 255) // 256 * 256
+    state = torch.empty((flat.n_nodes, chunk), dtype=torch.int16, device=device)
+    _lib.check(lib.cevb_stoch_map_sets(
+        _lib.ptr(pw), S, 7 * n * ldq, _lib.ptr(d_set), _lib.ptr(d_bn), n, _lib.ptr(d_root),
+        flat.n_nodes, _lib.ptr(d_parent), _lib.ptr(d_pre), _lib.ptr(d_len),
+        ctypes.c_ulonglong(seed & (2 ** 64 - 1)), rep_begin, rep_end, n_bins, _lib.ptr(hist),
+        _lib.ptr(sums), _lib.ptr(state), chunk, _lib.ptr(n_events), st), "cevb_stoch_map_sets")
+    if return_device:
+        return hist, sums, n_events
+    return finalize(flat, hist, sums, n_events, n_reps, n_bins)
+
+
 def finalize(flat, hist, sums, n_events, n_reps, n_bins):
     h = hist.cpu().numpy().astype(np.int64)
     h[:, :, 0] = n_reps - h[:, :, 1:].sum(axis=2)
@@ -130,18 +171,19 @@ def _root_distribution(mapper, n):
 def run_stochastic_mapping(mapper):
     """Backs StochasticMapper.perform_stochastic_mapping (AR:523-590)."""
     model = mapper.model
-    if model.branch_params:
-        raise NotImplementedError("branch-specific parameters are not on the device path yet "
-                                  "(SURVEY.md section 8 row f4)")
     n = model.max_chr + 1
     flat = FlatTree(mapper.tree, {}, model.max_chr)
     bn = model.params.get('base_number')
     bn = int(bn) if (bn and bn > 0) else 0
-    res = simulate(flat, params_to_row(model.params), n, _root_distribution(mapper, n),
-                   mapper.num_mappings, mapper._draw_seed(), base_number=bn, n_bins=mapper.n_bins)
+    rows, node_set = params_to_row(model.params), None
+    if model.branch_params:      # AR:569: the branch above a node may have its own parameters
+        rows, node_set = branch_parameter_sets(model, flat)
+    res = simulate(flat, rows, n, _root_distribution(mapper, n), mapper.num_mappings,
+                   mapper._draw_seed(), base_number=bn, n_bins=mapper.n_bins, node_set=node_set)
     if res.overflowed():   # a branch with >= n_bins-1 events of one type in some replicate
-        res = simulate(flat, params_to_row(model.params), n, _root_distribution(mapper, n),
-                       mapper.num_mappings, mapper._draw_seed(), base_number=bn, n_bins=mapper.n_bins * 16)
+        res = simulate(flat, rows, n, _root_distribution(mapper, n), mapper.num_mappings,
+                       mapper._draw_seed(), base_number=bn, n_bins=mapper.n_bins * 16,
+                       node_set=node_set)
     mapper.last_result = res
     summary = {}
     for k, node in enumerate(flat.nodes):

@@ -236,6 +236,17 @@ int cevb_stoch_map(const double* q, int n, const double* root_probs, int n_nodes
                    uint16_t* state_scratch, long long rep_chunk, unsigned long long* n_events,
                    void* stream);
 
+/* Branch-specific parameter sets (set_branch_parameters, AR:67-73; used by the mapper at AR:569):
+ * q [n_sets][...] rate matrices q_stride doubles apart, node_set [n_nodes] the set of the branch
+ * above each node, base_numbers [n_sets] (0 = None).  Everything else as cevb_stoch_map; the
+ * compact tables of all sets must fit in shared memory (about 15 sets at n = 101). */
+int cevb_stoch_map_sets(const double* q, int n_sets, long long q_stride, const int32_t* node_set,
+                        const int32_t* base_numbers, int n, const double* root_probs, int n_nodes,
+                        const int32_t* parent, const int32_t* preorder, const double* branch_len,
+                        unsigned long long seed, long long rep_begin, long long rep_end, int n_bins,
+                        uint32_t* hist, unsigned long long* sums, uint16_t* state_scratch,
+                        long long rep_chunk, unsigned long long* n_events, void* stream);
+
 /* One branch, one replicate, with every event recorded: replaces
  * StochasticMapper.simulate_events_on_branch, AR:467-521.  ev_* hold max_events entries;
  * out[0] = number of events simulated (may exceed max_events), out[1] = end state. */

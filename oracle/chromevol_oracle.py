@@ -271,12 +271,15 @@ def simulate_branch(Q, start_state, branch_length, rng, base_number=None):
     return counts, state
 
 
-def stochastic_mapping_counts(tree, Q, root_probs, num_mappings, rng, base_number=None):
+def stochastic_mapping_counts(tree, Q, root_probs, num_mappings, rng, base_number=None,
+                              branch_q=None):
     """Per-replicate event counts -- AR:523-576.
 
     Returns (branch_nodes in preorder, counts[num_mappings, n_branches, 8]).  Branches with
-    dist None/<=0 copy the parent state and record no events (AR:562-566).
+    dist None/<=0 copy the parent state and record no events (AR:562-566).  branch_q maps
+    id(node) -> (Q, base_number) for branches with their own parameters (AR:569).
     """
+    branch_q = branch_q or {}
     root = tree.get_tree_root()
     order = [nd for nd in tree.traverse("preorder") if not nd.is_root()]
     index = {id(nd): k for k, nd in enumerate(order)}
@@ -290,7 +293,8 @@ def stochastic_mapping_counts(tree, Q, root_probs, num_mappings, rng, base_numbe
             if t is None or t <= 0:
                 states[id(nd)] = start
                 continue
-            c, end = simulate_branch(Q, start, t, rng, base_number)
+            q_here, bn_here = branch_q.get(id(nd), (Q, base_number))
+            c, end = simulate_branch(q_here, start, t, rng, bn_here)
             out[rep, index[id(nd)]] = c
             states[id(nd)] = end
     return order, out

@@ -69,3 +69,31 @@ def test_objective_and_classify_live(AR):
         for b in range(0, 12):
             for bn in (None, 3):
                 assert mapper._classify_event(a, b, {"base_number": bn}) == O.classify_event(a, b, bn)
+
+
+def test_branch_specific_parameters_live(AR):
+    """set_branch_parameters (AR:67-73) + branch_params.get(id(child), params) in the up-pass
+    (AR:230-233): the oracle's branch_params argument against the reference itself."""
+    from ete3 import Tree
+    from chromevol_enhanced_b200 import synthetic
+    tree = synthetic.random_tree(30, seed=5)
+    counts = synthetic.simulate_tip_counts(tree, 24, seed=6)
+    nw = tree.write(dist_formatter="%.17g")
+    t_ref, t_or = Tree(nw, format=1), Tree(nw, format=1)
+    model = AR.ChromEvolutionModel(24, custom_params={"gain": 0.4})
+    ref_nodes = [nd for nd in t_ref.traverse() if not nd.is_root()]
+    or_nodes = [nd for nd in t_or.traverse() if not nd.is_root()]
+    overrides = {}
+    for k, (a, b) in enumerate(zip(ref_nodes, or_nodes)):
+        if k % 3 == 0:
+            kw = {"gain": 1.5, "dupl": 0.3} if k % 2 == 0 else {"loss": 2.0, "base_number": 5}
+            model.set_branch_parameters(id(a), **kw)
+            overrides[id(b)] = O.default_params(**{"gain": 0.4, **kw})
+    calc = AR.ChromEvolLikelihoodCalculator(t_ref, counts, model)
+    calc.set_root_frequencies(np.ones(25) / 25)
+    ll_ref = calc.calculate_total_log_likelihood()
+    ll, vectors, _ = O.log_likelihood(t_or, counts, 24, O.default_params(gain=0.4), np.ones(25) / 25,
+                                      branch_params=overrides)
+    assert ll == ll_ref
+    for a, b in zip(t_ref.traverse(), t_or.traverse()):
+        assert np.array_equal(calc.likelihoods[id(a)], vectors[id(b)])
