@@ -109,3 +109,25 @@ def test_branch_specific_mapper_matches_oracle_simulator():
             n_tests += 1
     assert n_tests > 15 and bn_events > 0
     assert worst < 5.0, worst
+
+
+def test_too_many_parameter_sets_for_the_mapper_is_an_error():
+    """The mapper keeps one compact rate table per set in shared memory; a model with more sets
+    than fit fails loudly (status + message), it does not fall back to anything."""
+    import torch
+    from chromevol_enhanced_b200 import _lib, mapper, synthetic
+    from chromevol_enhanced_b200.flatten import FlatTree
+    N = 100
+    tree = synthetic.random_tree(40, seed=1)
+    flat = FlatTree(tree, {}, N)
+    S = 40
+    rows = np.tile(np.array([0.1, 0.1, 0.05, 0.01, 0.01, 0.01, 0.01, 0.01, 0.0]), (S, 1))
+    rows[:, 0] += np.arange(S) * 0.01
+    node_set = np.arange(flat.n_nodes) % S
+    with pytest.raises(_lib.CevbError, match="shared memory"):
+        mapper.simulate(flat, rows, N + 1, np.ones(N + 1) / (N + 1), 1000, seed=1, node_set=node_set)
+    # a number of sets that fits runs
+    res = mapper.simulate(flat, rows[:6], N + 1, np.ones(N + 1) / (N + 1), 2000, seed=1,
+                          node_set=np.arange(flat.n_nodes) % 6)
+    assert res.n_events > 0 and not res.overflowed()
+    torch.cuda.synchronize()

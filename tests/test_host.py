@@ -124,3 +124,36 @@ def test_synthetic_generators_are_seeded():
     assert len({nd.dist for nd in a.traverse()}) == 99
     r1, r2 = synthetic.random_param_rows(8, 4, corners=2), synthetic.random_param_rows(8, 4, corners=2)
     assert np.array_equal(r1, r2) and abs(r1[-1, 7]) == 1.0
+
+
+def test_branch_parameter_sets_groups_identical_overrides():
+    """Host logic of SURVEY 8 row f4: distinct parameter sets and the per-node set index follow
+    ``branch_params.get(id(node), params)`` (AR:230-233); set 0 is the model-wide set and equal
+    override dicts share a set."""
+    from chromevol_enhanced_b200.engine import branch_parameter_sets, params_to_row
+    from chromevol_enhanced_b200.flatten import FlatTree
+    tree = make_tree("((A:0.1,B:0.2)X:0.3,(C:0.1,D:0.4)Y:0.2,E:0.5);")
+    flat = FlatTree(tree, {"A": 3, "B": 4, "C": 5, "D": 6, "E": 7}, 12)
+
+    class Model:
+        params = {"gain": 0.1, "loss": 0.2, "dupl": 0.0, "demidupl_gain": 0.0, "demidupl_loss": 0.0,
+                  "base_number_gain": 0.0, "base_number_loss": 0.0, "linear_rate": 0.0,
+                  "base_number": None}
+        branch_params = {}
+
+    by_name = {nd.name: nd for nd in flat.nodes}
+    m = Model()
+    rows, node_set = branch_parameter_sets(m, flat)
+    assert rows.shape == (1, 9) and not node_set.any()
+    fast = dict(m.params, gain=2.0)
+    other = dict(m.params, loss=1.0, base_number=4)
+    m.branch_params = {id(by_name["A"]): fast, id(by_name["Y"]): dict(fast), id(by_name["E"]): other,
+                       id(by_name["C"]): dict(m.params)}            # an override equal to the default
+    rows, node_set = branch_parameter_sets(m, flat)
+    assert rows.shape == (3, 9)
+    assert np.array_equal(rows[0], params_to_row(m.params))
+    assert np.array_equal(rows[1], params_to_row(fast)) and np.array_equal(rows[2], params_to_row(other))
+    idx = {nd.name: k for k, nd in enumerate(flat.nodes)}
+    assert node_set[idx["A"]] == 1 and node_set[idx["Y"]] == 1 and node_set[idx["E"]] == 2
+    assert node_set[idx["C"]] == 0 and node_set[idx["B"]] == 0 and node_set[idx["X"]] == 0
+    assert rows[2, 8] == 4.0 and rows[0, 8] == 0.0
