@@ -20,6 +20,9 @@ class CevbError(RuntimeError):
     pass
 
 
+MAX_STATES = 288     # CEVB_MAX_N in include/chromevol_b200.h: largest matrix order of the kernels
+
+
 _PROTOTYPES = {
     "cevb_abi_version": (_c.c_int, []),
     "cevb_device_info": (_c.c_int, [_c.POINTER(_c.c_int), _c.POINTER(_c.c_int), _c.POINTER(_c.c_int),
@@ -85,7 +88,7 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    path = os.environ.get("CEVB_LIB") or _build.LIB_PATH     # CEVB_LIB: development builds only
     if not os.path.exists(path):
         if not build_if_missing:
             raise CevbError(f"CUDA extension not built: {path}")

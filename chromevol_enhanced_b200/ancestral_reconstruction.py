@@ -86,6 +86,69 @@ class ChromEvolutionModel:
         return np.ascontiguousarray(P[0, 0])
 
 
+class _NodeVectors(dict):
+    """The calculator's memo ``likelihoods`` (id(node) -> ndarray[n], AR:178) after a device
+    evaluation.  The vectors stay on the device until something reads the memo: the optimiser
+    only needs the scalar log-likelihood (AR:359-361), so an objective call copies 8 bytes, not
+    every node vector.  The first read runs ``fill`` (a device -> host copy, preceded by a
+    re-evaluation if another call has overwritten the device buffer since)."""
+
+    def __init__(self, fill, logl):
+        super().__init__()
+        self._fill = fill
+        self.logl = logl
+
+    def _load(self):
+        fill, self._fill = self._fill, None
+        if fill is not None:
+            super().update(fill())
+
+    @property
+    def pending(self):
+        return self._fill is not None
+
+    def __getitem__(self, key):
+        self._load()
+        return super().__getitem__(key)
+
+    def __contains__(self, key):
+        self._load()
+        return super().__contains__(key)
+
+    def __len__(self):
+        self._load()
+        return super().__len__()
+
+    def __iter__(self):
+        self._load()
+        return super().__iter__()
+
+    def get(self, key, default=None):
+        self._load()
+        return super().get(key, default)
+
+    def keys(self):
+        self._load()
+        return super().keys()
+
+    def values(self):
+        self._load()
+        return super().values()
+
+    def items(self):
+        self._load()
+        return super().items()
+
+    def __eq__(self, other):
+        self._load()
+        return dict.__eq__(self, other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        return "<node vectors on the device>" if self.pending else dict.__repr__(self)
+
+
 class ChromEvolLikelihoodCalculator:
     """Felsenstein pruning on the device (AR:168-322)."""
 
@@ -97,6 +160,7 @@ class ChromEvolLikelihoodCalculator:
         self.root_frequencies = None
         self._flat = None
         self._flat_key = None
+        self._content = None
         self._engine = None
         self._het_engine = None      # materialised-path engine for branch-specific parameter sets
         self._het_key = None
@@ -104,19 +168,42 @@ class ChromEvolLikelihoodCalculator:
 
     # -- device state ---------------------------------------------------------------------
     def refresh(self):
-        """Drop the cached flattened tree (call after editing the tree or the counts dict)."""
+        """Drop the cached flattened tree.  Not needed after editing branch lengths, counts or
+        the children lists: every evaluation compares those with what was flattened."""
         self._flat = None
         self._engine = None
         self._het_engine = None
         self.likelihoods = {}
 
+    def _content_snapshot(self):
+        """What the device copy of the tree depends on, cheap enough to take on every evaluation
+        (about 0.1 ms for 1,000 taxa): branch lengths, child lists and the counts of the leaves.
+        The reference re-reads all of them on every call (AR:201-227)."""
+        nodes = self._flat.nodes
+        get = self.data.get if self.data is not None else (lambda name: None)
+        return ([nd.dist for nd in nodes], [nd.children for nd in nodes],
+                [len(nd.children) for nd in nodes], [get(nm) for nm in self._flat.leaf_names])
+
     def _device_engine(self):
-        key = (id(self.tree), id(self.data), len(self.data) if self.data is not None else 0,
-               self.model.max_chr)
+        key = (id(self.tree), id(self.data), self.model.max_chr)
+        if self._engine is not None and self._flat_key == key:
+            try:
+                same = self._content_snapshot() == self._content
+            except Exception:  # noqa: BLE001 - exotic tree objects: re-flatten
+                same = False
+            if not same:
+                self._engine = None
         if self._engine is None or self._flat_key != key:
+            if self.model.max_chr + 1 > _lib.MAX_STATES:
+                raise _lib.CevbError(
+                    f"max_chromosome_number={self.model.max_chr} needs {self.model.max_chr + 1} "
+                    f"states; the device kernels support at most {_lib.MAX_STATES} "
+                    f"(CEVB_MAX_N in include/chromevol_b200.h)")
             self._flat = FlatTree(self.tree, self.data, self.model.max_chr)
             self._engine = LikelihoodEngine(self._flat)
+            self._het_engine = None
             self._flat_key = key
+            self._content = self._content_snapshot()
         return self._engine
 
     def _has_branch_params(self):
@@ -133,39 +220,60 @@ class ChromEvolLikelihoodCalculator:
                             f"{len(frequencies) if frequencies is not None else 'None'}")
             self.root_frequencies = np.ones(n) / n
 
+    def _evaluate(self, spec):
+        """Run the device evaluation described by ``spec`` and return (engine, logL)."""
+        if spec[0] == "sets":
+            _, rows, node_set, root = spec
+            if self._het_engine is None or self._het_key != self._flat_key:
+                self._het_engine = LikelihoodEngine(self._flat, path="materialised")
+                self._het_key = self._flat_key
+            eng = self._het_engine
+            logl = float(eng.log_likelihood_branch_sets(rows, node_set, root_freq=root).item())
+        else:
+            _, row, root = spec
+            eng = self._engine
+            logl = float(eng.log_likelihood(row[None, :], root_freq=root)[0].item())
+        return eng, logl
+
     def _up_pass(self):
-        """One device evaluation; fills ``likelihoods`` (id(node) -> ndarray) like the memo dict."""
+        """One device evaluation.  ``likelihoods`` becomes a memo that reads the node vectors back
+        only when something asks for them (the optimiser never does)."""
         if self.root_frequencies is None:
             self.set_root_frequencies(None)
+        self._device_engine()
+        root = np.array(self.root_frequencies, dtype=np.float64, copy=True)
         if self._has_branch_params():
-            return self._up_pass_branch_sets()
-        eng = self._device_engine()
-        logl = eng.log_likelihood(params_to_row(self.model.params)[None, :],
-                                  root_freq=self.root_frequencies)
-        vec = eng.node_vectors(0).cpu().numpy()
-        self.likelihoods = {id(nd): vec[k] for k, nd in enumerate(self._flat.nodes)}
-        self._last_logl = float(logl[0].item())
-        return self._last_logl
+            # branch-specific parameters (set_branch_parameters, AR:67-73): every distinct set's
+            # matrices on the device, one pruning pass over the per-branch selection
+            rows, node_set = branch_parameter_sets(self.model, self._flat)
+            spec = ("sets", rows, node_set, root)
+        else:
+            spec = ("one", params_to_row(self.model.params), root)
+        eng, logl = self._evaluate(spec)
+        self._last_logl = logl
+        self._last_eval = (eng, eng.eval_token, spec)
+        flat = self._flat
+
+        def fill(last=self._last_eval):
+            vec = self._resident_vectors(last).cpu().numpy()
+            return {id(nd): vec[k] for k, nd in enumerate(flat.nodes)}
+
+        self.likelihoods = _NodeVectors(fill, logl)
+        return logl
+
+    def _resident_vectors(self, last):
+        """Device node vectors of the evaluation ``last``; evaluated again when another call
+        (a batch, a gradient, another model) has used the engine's buffers since."""
+        eng, token, spec = last
+        if eng.eval_token != token:
+            eng, _ = self._evaluate(spec)
+            self._last_eval = (eng, eng.eval_token, spec)
+        return eng.node_vectors(0)
 
     def branch_parameter_sets(self):
         """(rows (S, 9), node_set (n_nodes,)) of a branch-heterogeneous model; set 0 = model.params."""
         self._device_engine()
         return branch_parameter_sets(self.model, self._flat)
-
-    def _up_pass_branch_sets(self):
-        """Branch-specific parameters (set_branch_parameters, AR:67-73): every distinct set's
-        matrices on the device, one pruning pass over the per-branch selection."""
-        self._device_engine()
-        if self._het_engine is None or self._het_key != self._flat_key:
-            self._het_engine = LikelihoodEngine(self._flat, path="materialised")
-            self._het_key = self._flat_key
-        rows, node_set = self.branch_parameter_sets()
-        eng = self._het_engine
-        logl = eng.log_likelihood_branch_sets(rows, node_set, root_freq=self.root_frequencies)
-        vec = eng.node_vectors(0).cpu().numpy()
-        self.likelihoods = {id(nd): vec[k] for k, nd in enumerate(self._flat.nodes)}
-        self._last_logl = float(logl.item())
-        return self._last_logl
 
     def calculate_likelihood_at_node(self, node):
         """Conditional likelihood vector of ``node`` (AR:189-249)."""
@@ -178,8 +286,15 @@ class ChromEvolLikelihoodCalculator:
         root = self.tree.get_tree_root()
         if self.root_frequencies is None:
             self.set_root_frequencies(None)
-        if id(root) in self.likelihoods and self.likelihoods:
-            total = np.sum(self.likelihoods[id(root)] * self.root_frequencies)
+        memo = self.likelihoods
+        if isinstance(memo, _NodeVectors) and memo.pending:
+            # the memo of the last device evaluation, not read back yet: the root vector is
+            # still on the device
+            vec = self._resident_vectors(self._last_eval)[self._flat.root].cpu().numpy()
+            total = np.sum(vec * self.root_frequencies)
+            return -np.inf if total <= 0 else np.log(total)
+        if memo and id(root) in memo:
+            total = np.sum(memo[id(root)] * self.root_frequencies)
             return -np.inf if total <= 0 else np.log(total)
         return self._up_pass()
 
@@ -205,24 +320,34 @@ class ChromEvolLikelihoodCalculator:
         return eng.log_likelihood(rows, root_freq=self.root_frequencies).cpu().numpy()
 
     def ancestral_state_reconstruction(self):
-        """argmax of the normalised up-pass vector at every node (AR:274-322)."""
+        """argmax of the normalised up-pass vector at every node (AR:274-322), taken from the
+        memo's vectors like the reference: the device copy of the evaluation that filled the
+        memo, or the host vectors when the memo was put there by a caller."""
         if not self.likelihoods:
             self.calculate_total_log_likelihood()
         eng = self._device_engine()
         flat = self._flat
-        # the vectors of the last evaluation are still resident; recompute if the memo came from
-        # somewhere else
-        if any(id(nd) not in self.likelihoods for nd in flat.nodes):
-            self._up_pass()
-        if self._has_branch_params():
-            eng = self._het_engine        # the engine that holds the vectors of the last up-pass
-        ml_count, ml_prob, probs = eng.ancestral_states(0, want_probs=True)
+        memo = self.likelihoods
+        if not isinstance(memo, _NodeVectors):
+            if any(id(nd) not in memo for nd in flat.nodes):
+                self._up_pass()             # partial memo: the reference would fill it (AR:300)
+                memo = self.likelihoods
+        if isinstance(memo, _NodeVectors):
+            vec = self._resident_vectors(self._last_eval)
+            which_engine = self._last_eval[0]
+            ml_count, ml_prob, probs = which_engine.ancestral_states_of(vec, want_probs=True)
+        else:
+            host = np.zeros((flat.n_nodes, eng.ldp))
+            for k, nd in enumerate(flat.nodes):
+                host[k, :eng.n] = memo[id(nd)]
+            vec = torch.as_tensor(host, device=eng.device)
+            ml_count, ml_prob, probs = eng.ancestral_states_of(vec, want_probs=True)
         ml_count = ml_count.cpu().numpy()
         ml_prob = ml_prob.cpu().numpy()
         probs = probs.cpu().numpy()
         for node in self.tree.traverse("preorder"):                       # AR:298
             k = flat.index.get(id(node))
-            if k is None or id(node) not in self.likelihoods:
+            if k is None:
                 continue
             node.add_features(ml_count=np.int64(ml_count[k]))
             node.add_features(ml_probability=np.float64(ml_prob[k]))
@@ -257,7 +382,14 @@ class ChromEvolOptimizer:
             if np.isinf(log_likelihood) or np.isnan(log_likelihood):
                 return 1e9
             return -log_likelihood
-        except Exception as e:  # noqa: BLE001 - the reference swallows everything here
+        except _lib.CevbError:
+            raise       # no device / unsupported size / launch failure: never a 1e10 "likelihood"
+        except RuntimeError as e:
+            if 'CUDA' in str(e) or isinstance(e, torch.cuda.OutOfMemoryError):
+                raise
+            logging.error(f"Error in objective function: {e} with params {params_vector}")
+            return 1e10
+        except Exception as e:  # noqa: BLE001 - numerical trouble is a penalty, as in AR:369-371
             logging.error(f"Error in objective function: {e} with params {params_vector}")
             return 1e10
 
@@ -541,7 +673,3 @@ def calculate_model_selection_criteria(tree, counts_dict, max_chr_num, root_prio
         except ValueError:
             logging.error("Could not determine best model due to invalid AIC/BIC values.")
     return results
-
-
-def _unused():  # keep linters quiet about imports used only for their side effects
-    return torch, _lib

@@ -24,13 +24,45 @@
 // (cevb_expm_plan) to the Pade kernel of expm.cu, whose P the combine kernel reads.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
+
+// Timing experiments only (tools/stub_build.py): -DCEVB_STUB=<mask> removes parts of the apply
+// kernel -- 1 epilogue arithmetic, 2 ring waits and copies, 4 the DMMAs of chunks >= 1, 8 the
+// per-row reduction and stores.  Results are wrong with any bit set; the product build has 0.
+#ifndef CEVB_STUB
+#define CEVB_STUB 0
+#endif
 
 namespace cevb {
 
 constexpr int F_KC = CEVB_TAYLOR_KC;       // chunks of 4 series coefficients (degrees 0..39)
 constexpr int F_JT = 13;                   // 8-column tiles per pass (104 columns)
 constexpr double F_TRUNC = CEVB_TAYLOR_TRUNC;  // truncation bound of the series (absolute, entries <= 1)
+
+// Layout of the coefficient table of one vector.  An ITEM is (row i, pass p): the up-to-13
+// 8-column tiles [13 p, 13 p + 13) of row i.  tc[item][chunk c][slot s][column 8][degree 4]:
+// 13 * 32 doubles per chunk, F_KC chunks per item, contiguous.  The tiles of an item are stored in
+// SLOT order: slots are handed out in the order in which tiles first hold a non-zero coefficient
+// (C_k of a sparse Q fills in slowly: a third of all (row, chunk, tile) triples of the N = 100
+// workload are structurally zero), so the tiles that matter at chunk c are exactly the slot prefix
+// [0, m(c)).  The kernels neither copy nor multiply the rest.  Per item four 64-bit words of
+// meta data follow the coefficient data of the vector:
+//   [0] perm:   nibble s = tile (within the pass) held by slot s
+//   [1] counts: nibble c = m(c), the active slot prefix of chunk c (0..13)
+//   [2] inv:    nibble t = slot of tile t
+//   [3] unused
+constexpr int F_CHUNK = F_JT * 32;         // doubles per (item, chunk)
+constexpr int F_ITEM = F_KC * F_CHUNK;     // doubles per item
+constexpr int F_META = 4;                  // 64-bit words per item
+__host__ __device__ inline int taylor_npass(int n) { return ((n + 7) / 8 + F_JT - 1) / F_JT; }
+__host__ __device__ inline size_t taylor_data_doubles(int n) {
+    return (size_t)n * taylor_npass(n) * F_ITEM;
+}
+__host__ __device__ inline size_t taylor_vec_doubles(int n) {
+    return taylor_data_doubles(n) + (size_t)n * taylor_npass(n) * F_META;
+}
 
 // The series is summed for the SHIFTED matrix (uniformisation): with mu = max(0, -min_i Q_ii),
 //     expm(Q t) = e^{-mu t} sum_k t^k C_k,   C_k = (Q + mu I)^k / k!.
@@ -160,25 +192,36 @@ __global__ void __launch_bounds__(128) q_structure_kernel(const double* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// C_0 = I, C_k = C_{k-1} (Q + mu I) / k, one CTA per (row i, vector b); row i of C_k only needs
-// row i of C_{k-1}.  Output layout tc[b][i][c][j][4]: chunk c holds degrees 4c..4c+3 interleaved per
-// column, exactly the B-operand fragment order of DMMA (lane 4g+t <- column g, degree t).
-constexpr int TCR = 4;   // rows of C_k per CTA of the coefficient kernel
+// C_0 = I, C_k = C_{k-1} (Q + mu I) / k, TCR rows per CTA; row i of C_k only needs row i of
+// C_{k-1}.  Output: the slot-ordered item layout described at the top of this file (inside a
+// tile: [column 8][degree 4], exactly the B-operand fragment order of DMMA, lane 4g+t <- column
+// g, degree t).  `dense` != 0 hands every tile its slot at chunk 0 in natural order (identity
+// permutation, m(c) = all tiles): the layout without sparsity, kept for A/B measurements.
+constexpr int TCR = 4;                                   // rows of C_k per CTA
+constexpr int TC_MAXPASS = ((CEVB_MAX_N + 7) / 8 + F_JT - 1) / F_JT;
 
 __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restrict__ pw,
                                                            const uint16_t* __restrict__ csc,
                                                            const uint8_t* __restrict__ csc_cnt,
                                                            const double* __restrict__ norms,
                                                            int n, int ldq, int npad, double t_max,
-                                                           double* __restrict__ tc) {
+                                                           int dense, double* __restrict__ tc) {
     extern __shared__ double shc[];
     double* cur = shc;                    // [TCR][npad]
     double* nxt = shc + TCR * npad;       // [TCR][npad]
     double* stg = shc + 2 * TCR * npad;   // [TCR][npad][4]
+    __shared__ uint8_t s_act[TCR][TC_MAXPASS * F_JT];     // tile holds a non-zero in this chunk
+    __shared__ uint8_t s_perm[TCR][TC_MAXPASS][16];       // slot -> tile of the pass
+    __shared__ int8_t s_slot[TCR][TC_MAXPASS][16];        // tile of the pass -> slot (-1: none yet)
+    __shared__ int s_nslot[TCR][TC_MAXPASS];
+    __shared__ unsigned long long s_counts[TCR][TC_MAXPASS];
     const int i0 = blockIdx.x * TCR, b = blockIdx.y, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nj = npad >> 3, npass = taylor_npass(n);
     const double* Q = pw + (size_t)b * CEVB_NPOW * n * ldq;
     const uint16_t* idx_c = csc + (size_t)b * 2 * CEVB_MAX_SPARSE * n;
     const uint8_t* cnt_c = csc_cnt + (size_t)b * 2 * n;
+    double* tcb = tc + (size_t)b * taylor_vec_doubles(n);
     const double mu = norms[(size_t)b * CEVB_NNORM + CEVB_NORM_SHIFT];
     // chunks any branch of this vector can need: the longest branch decides (all of them when
     // it has to be scaled and squared, or when the caller gives no bound)
@@ -216,6 +259,15 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
     for (int j = tid; j < npad; j += 128) {
 #pragma unroll
         for (int r = 0; r < TCR; ++r) cur[r * npad + j] = (j == i0 + r) ? 1.0 : 0.0;
+    }
+    if (tid < TCR * TC_MAXPASS) {
+        const int r = tid / TC_MAXPASS, p = tid - r * TC_MAXPASS;
+        s_nslot[r][p] = 0;
+        s_counts[r][p] = 0ull;
+        for (int q = 0; q < 16; ++q) {
+            s_slot[r][p][q] = -1;
+            s_perm[r][p][q] = 0;
+        }
     }
     // the longest sparse column among this warp's threads bounds the unrolled product below
     // (typically 6-8 of the 12 slots are in use)
@@ -270,18 +322,87 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
         }
         __syncthreads();
         if ((k & 3) == 3) {
+            const int c = k >> 2;
+            // which tiles of this chunk hold a non-zero (a tile is 32 contiguous doubles of stg;
+            // NaN counts as non-zero)
+            for (int x = warp; x < TCR * nj; x += 4) {
+                const int r = x / nj, jt = x - r * nj;
+                const double v = stg[((size_t)r * npad + jt * 8) * 4 + lane];
+                const int any = __any_sync(0xffffffffu, !(v == 0.0));
+                if (lane == 0) s_act[r][jt] = (uint8_t)any;
+            }
+            __syncthreads();
+            // newly active tiles take the next slots of their item
+            if (tid < TCR * npass) {
+                const int r = tid / npass, p = tid - r * npass;
+                int ns = s_nslot[r][p];
+                for (int tl = 0; tl < F_JT; ++tl) {
+                    const int jt = p * F_JT + tl;
+                    if (jt < nj && s_slot[r][p][tl] < 0 && (dense || s_act[r][jt])) {
+                        s_slot[r][p][tl] = (int8_t)ns;
+                        s_perm[r][p][ns] = (uint8_t)tl;
+                        ++ns;
+                    }
+                }
+                s_nslot[r][p] = ns;
+                // chunk 0 is multiplied by straight-line code for 0, 3, 6, 9 or 13 slots (the
+                // apply kernel interleaves it with an epilogue): its count is rounded up; the
+                // extra slots hold zeros
+                int cnt = ns;
+                if (c == 0 && ns > 0) cnt = ns <= 3 ? 3 : (ns <= 6 ? 6 : (ns <= 9 ? 9 : F_JT));
+                s_counts[r][p] |= (unsigned long long)cnt << (4 * c);
+            }
+            __syncthreads();
+            // write-out in slot order; slots beyond the active prefix hold zeros at this chunk
             for (int r = 0; r < TCR; ++r) {
                 if (i0 + r >= n) break;
-                double2* dst = reinterpret_cast<double2*>(
-                    tc + (((size_t)b * n + i0 + r) * F_KC + (k >> 2)) * npad * 4);
-                const double2* src = reinterpret_cast<const double2*>(stg + (size_t)r * npad * 4);
-                for (int x = tid; x < npad * 2; x += 128) dst[x] = src[x];
+                for (int p = 0; p < npass; ++p) {
+                    const int ns = s_nslot[r][p];
+                    double2* dst = reinterpret_cast<double2*>(
+                        tcb + ((size_t)((i0 + r) * npass + p) * F_KC + c) * F_CHUNK);
+                    for (int x = tid; x < F_JT * 16; x += 128) {
+                        const int sl = x >> 4, rem = x & 15;   // rem = column * 2 + half
+                        double2 v = make_double2(0.0, 0.0);
+                        if (sl < ns) {
+                            const int jt = p * F_JT + s_perm[r][p][sl];
+                            v = *reinterpret_cast<const double2*>(
+                                stg + ((size_t)r * npad + jt * 8) * 4 + rem * 2);
+                        }
+                        dst[x] = v;
+                    }
+                }
             }
             __syncthreads();
         }
         double* sw = cur;
         cur = nxt;
         nxt = sw;
+    }
+    // meta data: tiles that never became active (and the tiles beyond npad) take the last slots
+    if (tid < TCR * npass) {
+        const int r = tid / npass, p = tid - r * npass;
+        if (i0 + r < n) {
+            int ns = s_nslot[r][p];
+            for (int tl = 0; tl < F_JT; ++tl) {
+                if (s_slot[r][p][tl] < 0) {
+                    s_slot[r][p][tl] = (int8_t)ns;
+                    s_perm[r][p][ns] = (uint8_t)tl;
+                    ++ns;
+                }
+            }
+            unsigned long long perm = 0ull, inv = 0ull;
+            for (int q = 0; q < F_JT; ++q) {
+                perm |= (unsigned long long)s_perm[r][p][q] << (4 * q);
+                inv |= (unsigned long long)(uint8_t)s_slot[r][p][q] << (4 * q);
+            }
+            unsigned long long* meta = reinterpret_cast<unsigned long long*>(
+                                           tcb + taylor_data_doubles(n)) +
+                                       (size_t)((i0 + r) * npass + p) * F_META;
+            meta[0] = perm;
+            meta[1] = s_counts[r][p];
+            meta[2] = inv;
+            meta[3] = 0ull;
+        }
     }
 }
 
@@ -347,13 +468,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase completes
+// (or the hint expires) instead of spinning.  The kernels are issue-bound -- a DMMA.8x8x4 holds
+// its scheduler for 16 cycles and every other warp instruction costs one -- so polling loops
+// of waiting warps are paid for by the warps that have work.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         " selp.u32 %0, 1, 0, p;\n}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
@@ -369,8 +494,10 @@ struct ApplyArgs {
     double* wr;               // [B][n_nodes][ldp]  row sums of the floored P (AR:154 divides)
     uint8_t* mode;            // [B][n_nodes]: only non-zero values are ever written
     int n_items, n, npad, ldp, ldl, n_nodes, rows_per_cta;
+    int npass;                // passes of 13 tiles per row (1 for n <= 104)
+    int meta_bytes;           // shared memory for the per-item meta data of a CTA's rows
     int stage_doubles_cap;    // doubles available for the coefficient ring
-    int pf_rows;              // rows pulled into L2 ahead of the shared-memory ring
+    int skew;                 // experiment: clocks by which every other warp of a scheduler starts late
     // EVAL mode: items index the branch-length array t_node [E]; the raw series value at
     // t 2^-s goes to X[slot[b * E + item]] (n rows of ldp doubles) for the squaring kernel
     const int32_t* slot;
@@ -399,24 +526,90 @@ constexpr int F_MAXSTAGE = 4;
 __host__ __device__ inline size_t apply_header_bytes(int eb) {
     return (size_t)((16 * F_MAXSTAGE + 4 * (3 * eb + 4) + 127) / 128) * 128;
 }
-// shared memory of the apply kernel: header (barriers, per-branch ints), the t^k table A
-// [eb/8][F_KC][32], the child vectors L [eb][ldl] and the ring of coefficient row tiles
-__host__ __device__ inline size_t apply_fixed_bytes(int eb, int ldl) {  // ldl = 0: no child vectors
-    return apply_header_bytes(eb) + sizeof(double) * ((size_t)(eb / 8) * F_KC * 32 + (size_t)eb * ldl);
+// shared memory of the apply kernel: header (barriers, per-branch ints), the meta data of the
+// CTA's items (16 bytes each), the t^k table A [eb/8][F_KC][32], the child vectors L [eb][ldl]
+// and the ring of coefficient item tiles
+__host__ __device__ inline size_t apply_meta_bytes(int items) {
+    return (size_t)((16 * items + 127) / 128) * 128;
+}
+__host__ __device__ inline size_t apply_fixed_bytes(int eb, int ldl, int items) {  // ldl = 0: no child vectors
+    return apply_header_bytes(eb) + apply_meta_bytes(items) +
+           sizeof(double) * ((size_t)(eb / 8) * F_KC * 32 + (size_t)eb * ldl);
+}
+
+// nibble q (compile-time) of the 64-bit word (lo, hi)
+template <int Q>
+__device__ __forceinline__ int nib(uint32_t lo, uint32_t hi) {
+    return (int)(((Q < 8 ? lo : hi) >> (4 * (Q & 7))) & 15u);
+}
+
+// DMMA switched off by a (warp-uniform) predicate: @!p leaves the accumulator untouched
+__device__ __forceinline__ void dmma884_if(double& c0, double& c1, double a, double b, int on) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.s32 p, %4, 0;\n"
+        " @p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n}\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b), "r"(on));
+}
+
+// One chunk of an item for the M active slots: the M B-fragment loads are issued back to back
+// and only then the M DMMAs (an LDS placed right before its DMMA, or right after a DMMA that
+// still has to read the same register, serialises the warp on the shared-memory latency -- see
+// tools/dmma_probe.py; the compiler barriers keep the two groups apart).
+template <int M>
+__device__ __forceinline__ void chunk_slots(double (&acc)[F_JT][2], const double* Bc, const double av) {
+    double bv[M > 0 ? M : 1];
+#pragma unroll
+    for (int sl = 0; sl < M; ++sl) bv[sl] = Bc[sl * 32];
+#pragma unroll
+    for (int sl = 0; sl < M; ++sl) dmma884(acc[sl][0], acc[sl][1], av, bv[sl]);
+}
+// the same for a run-time slot count m (warp-uniform): a compare tree over the 13 straight-line
+// variants -- four compare-and-branch pairs per chunk, no per-slot predicates
+__device__ __forceinline__ void chunk_dispatch(const int m, double (&acc)[F_JT][2], const double* Bc,
+                                               const double av) {
+    if (m > 6) {
+        if (m > 9) {
+            if (m > 11) {
+                if (m > 12) chunk_slots<13>(acc, Bc, av);
+                else chunk_slots<12>(acc, Bc, av);
+            } else {
+                if (m > 10) chunk_slots<11>(acc, Bc, av);
+                else chunk_slots<10>(acc, Bc, av);
+            }
+        } else {
+            if (m > 8) chunk_slots<9>(acc, Bc, av);
+            else if (m > 7) chunk_slots<8>(acc, Bc, av);
+            else chunk_slots<7>(acc, Bc, av);
+        }
+    } else {
+        if (m > 3) {
+            if (m > 5) chunk_slots<6>(acc, Bc, av);
+            else if (m > 4) chunk_slots<5>(acc, Bc, av);
+            else chunk_slots<4>(acc, Bc, av);
+        } else {
+            if (m > 2) chunk_slots<3>(acc, Bc, av);
+            else if (m > 1) chunk_slots<2>(acc, Bc, av);
+            else if (m > 0) chunk_slots<1>(acc, Bc, av);
+        }
+    }
 }
 
 // One CTA: vector b = blockIdx.z, branches [blockIdx.x * EB, +EB) of the launch's item list
 // (EB = NW * G * 8), rows [blockIdx.y * rows_per_cta, +rows_per_cta) of every P.  NW consumer
-// warps each own G groups of 8 branches and keep the G x 13 accumulator tiles of the current
-// row in registers; one extra producer warp streams the coefficient rows (the same tile for
-// all consumers) through a ring of shared-memory stages with full/empty mbarriers, so the
-// consumers drift apart and one warp's epilogue overlaps another warp's DMMAs.
+// warps each own a group of 8 branches and keep the 13 accumulator tiles of the current item
+// (row, pass) in registers; one extra producer warp streams the coefficient items (the same
+// tile for all consumers) through a ring of shared-memory stages with full/empty mbarriers,
+// so the consumers drift apart and one warp's epilogue overlaps another warp's DMMAs.
+// Only the ACTIVE slot prefix of every (item, chunk) is copied and multiplied (see the layout
+// notes at the top of the file): slot s of an item holds tile perm[s].
 // MODE APPLY_LEAF: every child of the launch is an observed leaf (one-hot L): the dot product
 // is a select of one accumulator and no child vectors are staged.  MODE APPLY_EVAL: no
 // epilogue arithmetic at all -- the series value at the scaled time t 2^-s of every pair with
 // t ||Q||_1 > theta is written out for the squaring kernel.
-template <int G, int NW, int MODE, bool FAST>
-__global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4))
+// ONEPASS: n <= 104, a row is a single item (compile-time trip count).
+template <int G, int NW, int MODE, bool ONEPASS>
+__global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? (MODE == APPLY_LEAF ? 3 : 2) : 4))
     taylor_apply_kernel(ApplyArgs a) {
     constexpr bool LEAF = MODE != APPLY_GENERAL;   // no child vectors in shared memory
     constexpr bool EVAL = MODE == APPLY_EVAL;
@@ -426,7 +619,8 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     constexpr int EB = NW * G * 8;
     const int b = blockIdx.z;
     const int e0 = blockIdx.x * EB;
-    const int n = a.n, npad = a.npad, ldl = a.ldl;
+    const int n = a.n, ldl = a.ldl;
+    const int npass = ONEPASS ? 1 : a.npass;
     const int i_begin = blockIdx.y * a.rows_per_cta;
     const int i_end = min(n, i_begin + a.rows_per_cta);
 
@@ -435,10 +629,25 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     int* s_child = reinterpret_cast<int*>(smraw + 16 * F_MAXSTAGE);
     int* s_code = s_child + EB;
     int* s_nc = s_code + EB;
-    double* As = reinterpret_cast<double*>(smraw + apply_header_bytes(EB));  // [EB/8][F_KC][32]
+    uint4* s_meta = reinterpret_cast<uint4*>(smraw + apply_header_bytes(EB));   // [rows][npass]
+    double* As = reinterpret_cast<double*>(smraw + apply_header_bytes(EB) + a.meta_bytes);  // [EB/8][F_KC][32]
     double* Ls = As + (size_t)(EB / 8) * F_KC * 32;                           // [EB][ldl] (not LEAF)
-    double* Bs = Ls + (LEAF ? 0 : (size_t)EB * ldl);                          // ring of row tiles
+    double* Bs = Ls + (LEAF ? 0 : (size_t)EB * ldl);                          // ring of item tiles
 
+    const double* tcb = a.tc + (size_t)b * taylor_vec_doubles(n);
+    {
+        // meta data of this CTA's items: (perm | inv, counts).  The leaf variant selects one
+        // accumulator by SLOT, so it wants the inverse permutation; the others map slot -> tile.
+        const unsigned long long* mg =
+            reinterpret_cast<const unsigned long long*>(tcb + taylor_data_doubles(n)) +
+            (size_t)i_begin * npass * F_META;
+        const int n_it = (i_end - i_begin) * npass;
+        for (int x = tid; x < n_it; x += blockDim.x) {
+            const unsigned long long w0 = mg[(size_t)x * F_META + (MODE == APPLY_LEAF ? 2 : 0)];
+            const unsigned long long w1 = mg[(size_t)x * F_META + 1];
+            s_meta[x] = make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
+        }
+    }
     for (int x = tid; x < EB; x += blockDim.x) {
         const int e = e0 + x;
         int nc = 0, child = -1, code = -2;
@@ -498,11 +707,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     }
     if (ck == 0) return;  // nothing on the fused path in this CTA (uniform across the CTA)
 
-    const int nj = npad >> 3;
-    // FAST (host-checked: npad == 104) is exactly one pass of 13 tiles: a compile-time trip count
-    // keeps the pass bookkeeping out of the registers of the row loop
-    const int npass = FAST ? 1 : (nj + F_JT - 1) / F_JT;
-    const int stage_doubles = ck * F_JT * 32;
+    const int stage_doubles = ck * F_CHUNK;
     int ns = a.stage_doubles_cap / stage_doubles;
     if (ns > F_MAXSTAGE) ns = F_MAXSTAGE;
 
@@ -520,6 +725,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
         // staged by the consumer warps while the producer already fills the ring.  Eight
         // independent loads per thread are in flight before the first store: a load-store loop
         // per element serialised ~25 HBM latencies per warp, 8-10 % of a level CTA's lifetime.
+        // Columns >= n (up to the 104 * npass the slots cover) hold zeros.
         const double unif = 1.0 / (double)n;  // AR:211
         const int total = EB * ldl;
         constexpr int NT = 32 * NW;
@@ -548,39 +754,38 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     }
 
     if (warp == NW) {
-        // ---- producer: one lane streams the (row, pass) tiles of the coefficient table.  Rows
-        // further ahead than the ring can be pulled into L2 first (cp.async.bulk.prefetch.L2,
-        // CEVB_PF rows); measured on B200 the step is 1 % faster WITHOUT it (the ring already
-        // covers the latency and the prefetches of ~600 resident CTAs crowd L2), so 0 is the default.
+        // ---- producer: one lane streams the items of the coefficient table; per chunk only the
+        // active slot prefix m(c) * 256 bytes is copied (runs of full chunks are one copy)
         if (lane != 0) return;
-        const double* tcb = a.tc + (size_t)b * n * F_KC * npad * 4;
-        const int PF_ROWS = a.pf_rows;
-        const uint32_t row_bytes = (uint32_t)npad * 4 * sizeof(double);
-        // 97 <= n <= 104: the ck chunks a row needs are contiguous in the table and in the
-        // stage, so a row is ONE bulk copy
-        const bool contiguous = (npad == F_JT * 8);
-        for (int i = i_begin; i < min(i_end, i_begin + PF_ROWS); ++i)
-            bulk_prefetch_l2(tcb + (size_t)i * F_KC * npad * 4, row_bytes * (uint32_t)ck);
+        if (CEVB_STUB & 2) return;
         int s = 0, use = 0;
         for (int i = i_begin; i < i_end; ++i) {
-            if (i + PF_ROWS < i_end)
-                bulk_prefetch_l2(tcb + (size_t)(i + PF_ROWS) * F_KC * npad * 4, row_bytes * (uint32_t)ck);
             for (int pass = 0; pass < npass; ++pass) {
+                const uint4 mt = s_meta[(i - i_begin) * npass + pass];
+                const unsigned long long cnts = ((unsigned long long)mt.w << 32) | mt.z;
+                uint32_t total = 0;
+                for (int c = 0; c < ck; ++c) total += (uint32_t)((cnts >> (4 * c)) & 15ull);
                 if (use > 0) {
                     const uint32_t par = (uint32_t)((use - 1) & 1);
-                    while (!mbar_try_wait(&empty[s], par)) __nanosleep(32);
+                    while (!mbar_try_wait(&empty[s], par)) {
+                    }
                 }
-                const int j0 = pass * F_JT * 8;
-                const int ncols = min(F_JT * 8, npad - j0);
-                const uint32_t bytes = (uint32_t)ncols * 4 * sizeof(double);
-                mbar_expect_tx(&full[s], bytes * (uint32_t)ck);
+                mbar_expect_tx(&full[s], total * 256u);
                 double* dst = Bs + (size_t)s * stage_doubles;
-                const double* src = tcb + ((size_t)i * F_KC * npad + j0) * 4;
-                if (contiguous) {
-                    bulk_g2s(dst, src, bytes * (uint32_t)ck, &full[s]);
-                } else {
-                    for (int c = 0; c < ck; ++c)
-                        bulk_g2s(dst + (size_t)c * F_JT * 32, src + (size_t)c * npad * 4, bytes, &full[s]);
+                const double* src = tcb + (size_t)(i * npass + pass) * F_ITEM;
+                int c = 0;
+                while (c < ck) {
+                    const int c_start = c;
+                    uint32_t bytes = 0;
+                    while (c < ck) {
+                        const uint32_t m = (uint32_t)((cnts >> (4 * c)) & 15ull);
+                        bytes += m * 256u;
+                        ++c;
+                        if (m != (uint32_t)F_JT) break;
+                    }
+                    if (bytes)
+                        bulk_g2s(dst + (size_t)c_start * F_CHUNK, src + (size_t)c_start * F_CHUNK, bytes,
+                                 &full[s]);
                 }
                 if (++s == ns) {
                     s = 0;
@@ -592,27 +797,39 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     }
     if (wk == 0) return;  // consumer warp without fused branches (not counted in `empty`)
 
+    if (a.skew > 0 && ((warp >> 2) & 1)) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)a.skew) {
+        }
+    }
     // ---- consumers (one group of 8 branches per warp)
     static_assert(G == 1, "the pipelined consumer loop keeps one group per warp");
-    const long long floor_bits = __double_as_longlong(1e-12);
+    // np.maximum(P, 1e-12) (AR:153) as a signed compare of the HIGH word only (one ISETP instead
+    // of two per value): negative values and everything below 1e-12 are replaced, NaN (positive
+    // high word) is kept like np.maximum keeps it.  Values that share the high word of 1e-12
+    // (0x3D719799) but lie below it -- within 4.4e-19 of 1e-12 -- are kept as they are: an
+    // absolute difference seven orders below the 1e-12 tolerance on P.
+    constexpr int floor_hi = 0x3D719799;
     const int xw = warp * 8 + g;                       // this lane's branch within the CTA
-    // LEAF: the tile / half of the row that holds column `code` of this lane's branch
-    int my_jt = -1, my_half = 0;
+    // LEAF: the pass / tile / half of the row that holds column `code` of this lane's branch
+    int my_pass = -1, my_tl = 0, my_half = 0;
     if (MODE == APPLY_LEAF) {
         const int code = s_code[xw];
         if (code >= 0 && ((code >> 1) & 3) == t4) {
-            my_jt = code >> 3;   // tile index along the whole row (pass * F_JT + jt)
+            my_pass = (code >> 3) / F_JT;
+            my_tl = (code >> 3) - my_pass * F_JT;
             my_half = code & 1;
         }
     }
-    const int sel0 = (my_jt >= 0 && my_half == 0) ? my_jt : -1;   // fast path (one pass)
-    const int sel1 = (my_jt >= 0 && my_half == 1) ? my_jt : -1;
-    constexpr bool fast = FAST;   // exactly one pass of 13 tiles (97 <= n <= 104), host-checked
-    // columns of the last tile that exist (kept as flags: two doubles here cost four registers
-    // of a loop that has none to spare)
-    const bool in_last0 = (F_JT - 1) * 8 + 2 * t4 < n;
-    const bool in_last1 = (F_JT - 1) * 8 + 2 * t4 + 1 < n;
-    const bool has_pad = npad != n;
+    // Every slot is floored at 1e-12, including the columns beyond n that the 13 * npass tiles
+    // cover (their accumulators are exact zeros): what they add to the row sum is taken out
+    // again at the end of the row (padfix = this lane's count of such columns times 1e-12).
+    double padfix;
+    {
+        int cnt = 0;
+        for (int j = 2 * t4; j < npass * F_JT * 8; j += 8) cnt += (j >= n) + (j + 1 >= n);
+        padfix = (double)cnt * 1e-12;
+    }
     const bool mine = s_nc[xw] > 0;
     const int my_child = s_child[xw];
     const unsigned int row_off = (unsigned)my_child * (unsigned)a.ldp;   // n_nodes * ldp < 2^31
@@ -620,56 +837,41 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     const double* Lbase = Ls + (size_t)xw * ldl + 2 * t4;
     double rs0 = 0.0, rs1 = 0.0, dt0 = 0.0, dt1 = 0.0;
     double acc[F_JT][2];
+#pragma unroll
+    for (int sl = 0; sl < F_JT; ++sl) acc[sl][0] = acc[sl][1] = 0.0;
 
-    // epilogue of one accumulator tile of the item (row i_e, pass pass_e): floor (AR:153), row
-    // sum, dot product with L_child -- or the raw store for the squaring kernel
-    auto epi_tile = [&](const int jt, double p0, double p1, const int i_e, const int pass_e,
-                        const int njt_e, const bool floored) {
+    // epilogue of accumulator slot SL of the item (row i_e, pass pass_e) whose slot -> tile map
+    // (or, LEAF, selected slot) is (pm_lo, pm_hi): floor (AR:153), row sum, dot product with
+    // L_child -- or the raw store for the squaring kernel
+    auto epi_tile = [&](auto SLc, double p0, double p1, const int i_e, const int pass_e,
+                        const uint32_t pm_lo, const uint32_t pm_hi, const bool floored) {
+        constexpr int SL = decltype(SLc)::value;
+        if (CEVB_STUB & 1) {
+            rs0 += p0;
+            return;
+        }
         if (EVAL) {
-            const int j = pass_e * F_JT * 8 + jt * 8 + 2 * t4;
-            if (mine && jt < njt_e && j < a.ldp)
+            const int jt = nib<SL>(pm_lo, pm_hi);
+            const int j = (pass_e * F_JT + jt) * 8 + 2 * t4;
+            if (mine && j < a.ldp)
                 *reinterpret_cast<double2*>(a.X + ((size_t)my_child * n + i_e) * a.ldp + j) =
                     make_double2(p0, p1);
             return;
         }
-        if (fast) {
-            // one pass of exactly 13 tiles (97 <= n <= 104): branch-free.  The padding columns
-            // of the last tile hold exact zeros (zero coefficients), so a "floor" of 0 removes
-            // them from the row sum.
-            if (!floored) {
-                const double f0 = (jt == F_JT - 1 && !in_last0) ? 0.0 : 1e-12;
-                const double f1 = (jt == F_JT - 1 && !in_last1) ? 0.0 : 1e-12;
-                p0 = (__double_as_longlong(p0) < floor_bits) ? f0 : p0;
-                p1 = (__double_as_longlong(p1) < floor_bits) ? f1 : p1;
-            }
-            rs0 += p0;
-            rs1 += p1;
-            if (MODE == APPLY_LEAF) {
-                dt0 = (jt == sel0) ? p0 : dt0;
-                dt0 = (jt == sel1) ? p1 : dt0;
-            } else {
-                const double2 l = *reinterpret_cast<const double2*>(Lbase + jt * 8);
-                dt0 = fma(p0, l.x, dt0);
-                dt1 = fma(p1, l.y, dt1);
-            }
-        } else if (jt < njt_e) {
-            const int j0 = pass_e * F_JT * 8;
-            if (__double_as_longlong(p0) < floor_bits) p0 = 1e-12;
-            if (__double_as_longlong(p1) < floor_bits) p1 = 1e-12;
-            if (has_pad && jt == njt_e - 1) {  // the tile that may hold padding columns
-                const int j = j0 + jt * 8 + 2 * t4;
-                if (j >= n) p0 = 0.0;
-                if (j + 1 >= n) p1 = 0.0;
-            }
-            rs0 += p0;
-            rs1 += p1;
-            if (MODE == APPLY_LEAF) {
-                if (jt == my_jt - pass_e * F_JT) dt0 = my_half ? p1 : p0;
-            } else {
-                const double2 l = *reinterpret_cast<const double2*>(Lbase + j0 + jt * 8);
-                dt0 = fma(p0, l.x, dt0);
-                dt1 = fma(p1, l.y, dt1);
-            }
+        if (!floored) {
+            p0 = (__double2hiint(p0) < floor_hi) ? 1e-12 : p0;
+            p1 = (__double2hiint(p1) < floor_hi) ? 1e-12 : p1;
+        }
+        rs0 += p0;
+        rs1 += p1;
+        if (MODE == APPLY_LEAF) {
+            // pm_lo = the slot of this lane's column in this item (-1: none)
+            dt0 = ((int)pm_lo == SL) ? (my_half ? p1 : p0) : dt0;
+        } else {
+            const int jt = nib<SL>(pm_lo, pm_hi);
+            const double2 l = *reinterpret_cast<const double2*>(Lbase + (pass_e * F_JT + jt) * 8);
+            dt0 = fma(p0, l.x, dt0);
+            dt1 = fma(p1, l.y, dt1);
         }
     };
     // end of a row: quad reduction and the two stores (the combine kernel forms d / r, AR:154).
@@ -678,8 +880,12 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     // read by the stores, so the warp keeps issuing.
     auto finish_row = [&](const int i_e) {
         if (EVAL) return;
+        if (CEVB_STUB & 8) {
+            rs0 = rs1 = dt0 = dt1 = 0.0;
+            return;
+        }
         double r0 = 0.0, r1 = 0.0, d0 = 0.0, d1 = 0.0;
-        dmma884(r0, r1, rs0 + rs1, 1.0);
+        dmma884(r0, r1, (rs0 + rs1) - padfix, 1.0);
         dmma884(d0, d1, dt0 + dt1, 1.0);
         if (t4 == 0 && mine) {
             // vector base: CTA-uniform 64-bit; row offset inside the vector: 32-bit per lane
@@ -692,62 +898,89 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     };
 
     // Software pipeline over the items (row, pass): while the first chunk of item q is issued
-    // to the tensor pipe, the finished accumulator tiles of item q-1 are read out one by one
+    // to the tensor pipe, the finished accumulator slots of item q-1 are read out one by one
     // and post-processed, so a warp keeps the FP64 pipe fed during its own epilogue.
     int s = 0;
     uint32_t par = 0;
-    int i_prev = 0, pass_prev = 0, njt_prev = 0;
+    int i_prev = 0, pass_prev = 0;
+    uint32_t pm_prev_lo = 0, pm_prev_hi = 0;
     bool have_prev = false;
 
     for (int i = i_begin; i < i_end; ++i) {
         for (int pass = 0; pass < npass; ++pass) {
-            const int njt = FAST ? F_JT : min(F_JT, nj - pass * F_JT);
-            mbar_wait(&full[s], par);
+            const uint4 mt = s_meta[(i - i_begin) * npass + pass];
+            uint32_t c_lo = mt.z, c_hi = mt.w;
+            if (!(CEVB_STUB & 2)) mbar_wait(&full[s], par);
             const double* Bq = Bs + (size_t)s * stage_doubles + lane;
-            // Per chunk: the 13 B-fragment loads are issued back to back into 13 registers and
-            // only then the 13 DMMAs (the compiler barriers keep ptxas from re-interleaving
-            // them: an LDS placed right before its DMMA, or right after a DMMA that still has to
-            // read the same register, serialises the warp on the shared-memory latency -- see
-            // tools/dmma_probe.py).  Tiles beyond njt (last pass of a wide row) multiply stale
-            // shared memory; their accumulators are never read.
-            double bv[F_JT];
-            {
-                const double av = Aw[0];
+            // chunk 0 is interleaved with the epilogue of the previous item, so its DMMAs are
+            // predicated per slot (SL < m(0)); the later chunks branch to the straight-line
+            // variant of their slot count
+            const int m0 = (int)(c_lo & 15u);
+            if (have_prev) {
+                // chunk 0 with the epilogue of the previous item between its DMMAs.  Straight-
+                // line variants for 3, 6, 9 or 13 slots (the table rounds m(0) up to one of
+                // them), so no per-slot predicate is needed.
+                auto chunk0 = [&](auto Mc) {
+                    constexpr int M = decltype(Mc)::value;
+                    const double av = Aw[0];
+                    double bv[M > 0 ? M : 1];
 #pragma unroll
-                for (int jt = 0; jt < F_JT; ++jt) bv[jt] = Bq[jt * 32];
-                asm volatile("" ::: "memory");
-#pragma unroll
-                for (int jt = 0; jt < F_JT; ++jt) {
-                    double p0 = acc[jt][0], p1 = acc[jt][1];
-                    if (fast && !EVAL) {
-                        // the floor consumes the old accumulator values, so no register copy is
-                        // needed before the DMMA overwrites the tile (AR:153; padding columns
-                        // hold exact zeros and get a "floor" of 0)
-                        const double f0 = (jt == F_JT - 1 && !in_last0) ? 0.0 : 1e-12;
-                        const double f1 = (jt == F_JT - 1 && !in_last1) ? 0.0 : 1e-12;
-                        p0 = (__double_as_longlong(p0) < floor_bits) ? f0 : p0;
-                        p1 = (__double_as_longlong(p1) < floor_bits) ? f1 : p1;
+                    for (int sl = 0; sl < M; ++sl) bv[sl] = Bq[sl * 32];
+                    asm volatile("" ::: "memory");
+                    auto step = [&](auto SLc) {
+                        constexpr int SL = decltype(SLc)::value;
+                        double p0 = acc[SL][0], p1 = acc[SL][1];
+                        if (!EVAL) {
+                            // the floor consumes the old accumulator values, so no register copy
+                            // is needed before the DMMA overwrites the slot (AR:153)
+                            p0 = (__double2hiint(p0) < floor_hi) ? 1e-12 : p0;
+                            p1 = (__double2hiint(p1) < floor_hi) ? 1e-12 : p1;
+                        }
+                        acc[SL][0] = 0.0;
+                        acc[SL][1] = 0.0;
+                        if (SL < M) dmma884(acc[SL][0], acc[SL][1], av, bv[SL < M ? SL : 0]);
+                        epi_tile(SLc, p0, p1, i_prev, pass_prev, pm_prev_lo, pm_prev_hi, true);
+                    };
+                    step(std::integral_constant<int, 0>{});
+                    step(std::integral_constant<int, 1>{});
+                    step(std::integral_constant<int, 2>{});
+                    step(std::integral_constant<int, 3>{});
+                    step(std::integral_constant<int, 4>{});
+                    step(std::integral_constant<int, 5>{});
+                    step(std::integral_constant<int, 6>{});
+                    step(std::integral_constant<int, 7>{});
+                    step(std::integral_constant<int, 8>{});
+                    step(std::integral_constant<int, 9>{});
+                    step(std::integral_constant<int, 10>{});
+                    step(std::integral_constant<int, 11>{});
+                    step(std::integral_constant<int, 12>{});
+                    asm volatile("" ::: "memory");
+                };
+                if (m0 <= 6) {
+                    if (m0 <= 3) {
+                        if (m0 == 0) chunk0(std::integral_constant<int, 0>{});
+                        else chunk0(std::integral_constant<int, 3>{});
+                    } else {
+                        chunk0(std::integral_constant<int, 6>{});
                     }
-                    acc[jt][0] = 0.0;
-                    acc[jt][1] = 0.0;
-                    dmma884(acc[jt][0], acc[jt][1], av, bv[jt]);
-                    if (have_prev) epi_tile(jt, p0, p1, i_prev, pass_prev, njt_prev, true);
+                } else {
+                    if (m0 <= 9) chunk0(std::integral_constant<int, 9>{});
+                    else chunk0(std::integral_constant<int, 13>{});
                 }
-                asm volatile("" ::: "memory");
+            } else {
+                chunk_dispatch(m0, acc, Bq, Aw[0]);   // first item: the accumulators are zero
             }
             for (int c = 1; c < wk; ++c) {
+                c_lo = __funnelshift_r(c_lo, c_hi, 4);
+                c_hi >>= 4;
+                const int m = (int)(c_lo & 15u);
                 const double av = Aw[(size_t)c * 32];
-                const double* Bc = Bq + (size_t)c * F_JT * 32;
-#pragma unroll
-                for (int jt = 0; jt < F_JT; ++jt) bv[jt] = Bc[jt * 32];
-                asm volatile("" ::: "memory");
-#pragma unroll
-                for (int jt = 0; jt < F_JT; ++jt) dmma884(acc[jt][0], acc[jt][1], av, bv[jt]);
-                asm volatile("" ::: "memory");
+                const double* Bc = Bq + (size_t)c * F_CHUNK;
+                if (!(CEVB_STUB & 4)) chunk_dispatch(m, acc, Bc, av);
             }
             // every shared-memory read of this stage has been consumed by an issued DMMA
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            if (lane == 0 && !(CEVB_STUB & 2)) mbar_arrive(&empty[s]);
             if (++s == ns) {
                 s = 0;
                 par ^= 1u;
@@ -756,12 +989,34 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
             have_prev = true;
             i_prev = i;
             pass_prev = pass;
-            njt_prev = njt;
+            if (MODE == APPLY_LEAF) {
+                // slot that holds this lane's observed column in this item
+                const uint32_t wsel = (my_tl < 8) ? mt.x : mt.y;
+                pm_prev_lo = (pass == my_pass) ? ((wsel >> (4 * (my_tl & 7))) & 15u) : 0xffffffffu;
+            } else {
+                pm_prev_lo = mt.x;
+                pm_prev_hi = mt.y;
+            }
         }
     }
     if (have_prev) {
-#pragma unroll
-        for (int jt = 0; jt < F_JT; ++jt) epi_tile(jt, acc[jt][0], acc[jt][1], i_prev, pass_prev, njt_prev, false);
+        auto last = [&](auto SLc) {
+            constexpr int SL = decltype(SLc)::value;
+            epi_tile(SLc, acc[SL][0], acc[SL][1], i_prev, pass_prev, pm_prev_lo, pm_prev_hi, false);
+        };
+        last(std::integral_constant<int, 0>{});
+        last(std::integral_constant<int, 1>{});
+        last(std::integral_constant<int, 2>{});
+        last(std::integral_constant<int, 3>{});
+        last(std::integral_constant<int, 4>{});
+        last(std::integral_constant<int, 5>{});
+        last(std::integral_constant<int, 6>{});
+        last(std::integral_constant<int, 7>{});
+        last(std::integral_constant<int, 8>{});
+        last(std::integral_constant<int, 9>{});
+        last(std::integral_constant<int, 10>{});
+        last(std::integral_constant<int, 11>{});
+        last(std::integral_constant<int, 12>{});
         finish_row(i_prev);
     }
 }
@@ -1062,27 +1317,33 @@ static int fused_query() {
     return 0;
 }
 
-template <int G, int NW, int MODE, bool FAST>
-static int launch_apply_fast(ApplyArgs& a, int B, cudaStream_t st);
-
-template <int G, int NW, int MODE>
-static int launch_apply_variant(ApplyArgs& a, int B, cudaStream_t st) {
-    if (MODE != APPLY_EVAL && a.npad == F_JT * 8) return launch_apply_fast<G, NW, MODE, true>(a, B, st);
-    return launch_apply_fast<G, NW, MODE, false>(a, B, st);
+// Development knobs, read from the environment ONCE (first use), never on the launch path:
+//   CEVB_TW / CEVB_TM / CEVB_TS   branch-count thresholds of the CTA shapes (launch_apply_shapes)
+//   CEVB_DENSE=1                  coefficient table without the sparse slot order (A/B runs)
+struct Tuning {
+    int tw, tm, ts, dense, skew;
+};
+static const Tuning& tuning() {
+    static const Tuning t = [] {
+        auto env = [](const char* name, int dflt) {
+            const char* v = getenv(name);
+            return v ? atoi(v) : dflt;
+        };
+        Tuning x;
+        x.tw = env("CEVB_TW", 300);   // wide: 15 consumer warps
+        x.tm = env("CEVB_TM", 100);   // medium: 7
+        x.ts = env("CEVB_TS", 8);     // small: 3, else 1
+        x.dense = env("CEVB_DENSE", 0);
+        x.skew = env("CEVB_SKEW", 0);
+        return x;
+    }();
+    return t;
 }
 
-template <int G, int NW, int MODE, bool FAST>
-static int launch_apply_fast(ApplyArgs& a, int B, cudaStream_t st) {
+template <int G, int NW, int MODE, bool ONEPASS>
+static int launch_apply_one(ApplyArgs& a, int B, cudaStream_t st) {
     constexpr int EB = NW * G * 8;
-    const size_t fixed = apply_fixed_bytes(EB, MODE != APPLY_GENERAL ? 0 : a.ldl);
-    const size_t one_stage = sizeof(double) * (size_t)F_KC * F_JT * 32;
-    if (fixed + one_stage > g_f_optin) return 1;  // does not fit: caller tries a smaller variant
-    size_t ring = g_f_optin - fixed;
-    size_t ring_max = (NW >= 15 ? F_MAXSTAGE : 1) * one_stage;  // narrow CTAs: more of them per SM
-    if (ring > ring_max) ring = ring_max;
-    a.stage_doubles_cap = (int)(ring / sizeof(double));
-    a.pf_rows = getenv("CEVB_PF") ? atoi(getenv("CEVB_PF")) : 0;
-    const size_t smem = fixed + ring;
+    // rows of every P are split over blockIdx.y when the launch has too few CTAs to fill the GPU
     const int gx = (a.n_items + EB - 1) / EB;
     const long long want = 4LL * g_f_sm;
     int ry = 1;
@@ -1093,12 +1354,34 @@ static int launch_apply_fast(ApplyArgs& a, int B, cudaStream_t st) {
     }
     a.rows_per_cta = (a.n + ry - 1) / ry;
     ry = (a.n + a.rows_per_cta - 1) / a.rows_per_cta;
+    a.meta_bytes = (int)apply_meta_bytes(a.rows_per_cta * a.npass);
+    const size_t fixed = apply_fixed_bytes(EB, MODE != APPLY_GENERAL ? 0 : a.ldl,
+                                           a.rows_per_cta * a.npass);
+    const size_t one_stage = sizeof(double) * (size_t)F_ITEM;
+    if (fixed + one_stage > g_f_optin) return 1;  // does not fit: caller tries a smaller variant
+    size_t ring = g_f_optin - fixed;
+    size_t ring_max = (NW >= 15 ? F_MAXSTAGE : 1) * one_stage;  // narrow CTAs: more of them per SM
+    if (ring > ring_max) ring = ring_max;
+    a.stage_doubles_cap = (int)(ring / sizeof(double));
+    a.skew = tuning().skew;
+    const size_t smem = fixed + ring;
     dim3 grid(gx, ry, B);
-    CEVB_CHECK_CUDA(cudaFuncSetAttribute(taylor_apply_kernel<G, NW, MODE, FAST>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    taylor_apply_kernel<G, NW, MODE, FAST><<<grid, 32 * (NW + 1), smem, st>>>(a);
+    // the opt-in shared-memory size of an instantiation is raised once (the largest request so far)
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        CEVB_CHECK_CUDA(cudaFuncSetAttribute(taylor_apply_kernel<G, NW, MODE, ONEPASS>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    taylor_apply_kernel<G, NW, MODE, ONEPASS><<<grid, 32 * (NW + 1), smem, st>>>(a);
     CEVB_CHECK_LAUNCH("taylor_apply_kernel");
     return 0;
+}
+
+template <int G, int NW, int MODE>
+static int launch_apply_variant(ApplyArgs& a, int B, cudaStream_t st) {
+    if (a.npass == 1) return launch_apply_one<G, NW, MODE, true>(a, B, st);
+    return launch_apply_one<G, NW, MODE, false>(a, B, st);
 }
 
 template <int MODE>
@@ -1106,15 +1389,13 @@ static int launch_apply_shapes(ApplyArgs& a, int B, cudaStream_t st) {
     // CTA shapes.  The kernel is latency-bound per warp (every warp alternates a DMMA phase and
     // an epilogue phase), so many narrow CTAs per SM beat few wide ones except for the long
     // all-leaves list, where wide CTAs share each coefficient tile among 128 branches.
-    // (thresholds measured on B200 with tools/level_probe.py; CEVB_TW / CEVB_TM / CEVB_TS override them)
+    // (thresholds measured on B200 with tools/level_probe.py)
     int rc = 1;
-    const int tw = getenv("CEVB_TW") ? atoi(getenv("CEVB_TW")) : 300;    // wide: 15 consumer warps
-    const int tm = getenv("CEVB_TM") ? atoi(getenv("CEVB_TM")) : 100;    // medium: 7
-    const int ts = getenv("CEVB_TS") ? atoi(getenv("CEVB_TS")) : 8;      // small: 3, else 1
-    if (a.n_items > tw) rc = launch_apply_variant<1, 15, MODE>(a, B, st);
-    if (rc == 1 && a.n_items > tm) rc = launch_apply_variant<1, 7, MODE>(a, B, st);
-    if (rc == 1 && a.n_items > ts) rc = launch_apply_variant<1, 3, MODE>(a, B, st);
-    if (rc == 1 && a.n_items > ts) rc = launch_apply_variant<1, 7, MODE>(a, B, st);  // large n
+    const Tuning& tn = tuning();
+    if (a.n_items > tn.tw) rc = launch_apply_variant<1, 15, MODE>(a, B, st);
+    if (rc == 1 && a.n_items > tn.tm) rc = launch_apply_variant<1, 7, MODE>(a, B, st);
+    if (rc == 1 && a.n_items > tn.ts) rc = launch_apply_variant<1, 3, MODE>(a, B, st);
+    if (rc == 1 && a.n_items > tn.ts) rc = launch_apply_variant<1, 7, MODE>(a, B, st);  // large n
     if (rc == 1) rc = launch_apply_variant<1, 1, MODE>(a, B, st);
     return rc;
 }
@@ -1249,7 +1530,11 @@ static int launch_apply(const double* tc, const double* norms, int B, int n, int
     a.tc = tc; a.norms = norms; a.items = items; a.t_node = nullptr; a.leaf_code = leaf_code;
     a.node_vec = node_vec; a.w = w; a.wr = wr; a.mode = mode;
     a.n_items = n_items; a.n = n; a.npad = round_up(n, 8); a.ldp = ldp_of(n); a.n_nodes = n_nodes;
-    a.ldl = a.npad + ((a.npad % 16) == 0 ? 8 : 0);
+    a.npass = taylor_npass(n);
+    // child vectors cover every column the 13 * npass tiles of a row address (zeros beyond n);
+    // a stride of 8 (mod 16) doubles keeps the epilogue's 16-byte loads conflict-free
+    a.ldl = a.npass * F_JT * 8;
+    if ((a.ldl % 16) == 0) a.ldl += 8;
     a.slot = nullptr; a.X = nullptr; a.E = plan.E;
     a.plan_nc = plan.nc; a.plan_tau = plan.tau; a.plan_a0 = plan.a0; a.branch_of = plan.branch_of;
     const int rc = leaf_only ? launch_apply_shapes<APPLY_LEAF>(a, B, st)
@@ -1265,9 +1550,7 @@ static int launch_apply(const double* tc, const double* norms, int B, int n, int
 
 using namespace cevb;
 
-extern "C" size_t cevb_taylor_doubles(int n) {
-    return (size_t)n * F_KC * round_up(n, 8) * 4;
-}
+extern "C" size_t cevb_taylor_doubles(int n) { return taylor_vec_doubles(n); }
 
 extern "C" int cevb_taylor_prepare(const double* pw, int B, int n, double t_max, double* norms,
                                    uint16_t* csc, uint8_t* csc_cnt, double* tc, void* stream) {
@@ -1282,10 +1565,14 @@ extern "C" int cevb_taylor_prepare(const double* pw, int B, int n, double t_max,
     CEVB_CHECK_LAUNCH("q_structure_kernel");
     dim3 grid((n + TCR - 1) / TCR, B);
     const size_t csm = sizeof(double) * 6 * TCR * (size_t)npad;
-    CEVB_CHECK_CUDA(cudaFuncSetAttribute(taylor_coeff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)csm));
+    static size_t coeff_attr = 0;
+    if (csm > coeff_attr) {
+        CEVB_CHECK_CUDA(cudaFuncSetAttribute(taylor_coeff_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+        coeff_attr = csm;
+    }
     taylor_coeff_kernel<<<grid, 128, csm, st>>>(
-        pw, csc, csc_cnt, norms, n, ldq_of(n), npad, t_max, tc);
+        pw, csc, csc_cnt, norms, n, ldq_of(n), npad, t_max, tuning().dense, tc);
     CEVB_CHECK_LAUNCH("taylor_coeff_kernel");
     return 0;
 }
@@ -1331,6 +1618,7 @@ extern "C" int cevb_taylor_matrices(const double* tc, const double* norms, const
     a.node_vec = nullptr; a.w = nullptr; a.wr = nullptr; a.mode = nullptr;
     a.n_items = E; a.n = n; a.npad = round_up(n, 8); a.ldp = ldp_of(n); a.n_nodes = 0;
     a.ldl = 0;
+    a.npass = taylor_npass(n);
     a.slot = slot; a.X = P; a.E = E;
     a.plan_nc = plan_nc; a.plan_tau = plan_tau; a.plan_a0 = plan_a0; a.branch_of = nullptr;
     int rc = launch_apply_shapes<APPLY_EVAL>(a, B, st);
@@ -1345,8 +1633,12 @@ extern "C" int cevb_taylor_matrices(const double* tc, const double* norms, const
         return -1;
     }
     CEVB_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
-    CEVB_CHECK_CUDA(cudaFuncSetAttribute(square_post_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t sq_attr = 0;
+    if (smem > sq_attr) {
+        CEVB_CHECK_CUDA(cudaFuncSetAttribute(square_post_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sq_attr = smem;
+    }
     long long grid = g_f_sm;
     if (grid > cap) grid = cap;
     square_post_kernel<<<(unsigned)grid, SQ_NT, smem, st>>>(P, work_s, count, cap, counter, n, a.ldp,

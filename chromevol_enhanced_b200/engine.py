@@ -184,6 +184,7 @@ class LikelihoodEngine:
         self._graphs = {}
         self.chunk = int(chunk)
         self.overflow_events = 0
+        self.eval_token = 0          # bumped by every evaluation that rewrites the resident vectors
         self._ws = None
         self._node_vec = None
         self._cap = 0
@@ -399,6 +400,7 @@ class LikelihoodEngine:
         if d_params.dim() == 1:
             d_params = d_params[None, :]
         B = d_params.shape[0]
+        self.eval_token += 1
         d_root = root_freq if torch.is_tensor(root_freq) else self.root_freq_tensor(root_freq)
         if (check_growth and 0 < B <= min(self.graph_max_batch, self.chunk) and self.path == "fused"
                 and self.squaring == "series" and self.stage_events is None and not self.keep_info):
@@ -505,6 +507,7 @@ class LikelihoodEngine:
         if node_set.shape != (f.n_nodes,) or node_set.min() < 0 or node_set.max() >= S:
             raise ValueError("node_set must hold one parameter-set index per node")
         d_root = root_freq if torch.is_tensor(root_freq) else self.root_freq_tensor(root_freq)
+        self.eval_token += 1
         self._ensure(S)
         ws = self._ws
         ws.params[:S].copy_(torch.as_tensor(rows, device=self.device))
@@ -551,8 +554,16 @@ class LikelihoodEngine:
 
     def ancestral_states(self, which=0, want_probs=True):
         """argmax states for vector `which` of the last chunk -> (ml_count, ml_prob, probs)."""
+        return self.ancestral_states_of(self._node_vec[which], want_probs)
+
+    def ancestral_states_of(self, vec, want_probs=True):
+        """argmax states (AR:298-320) of conditional-likelihood vectors (n_nodes, ldp) or
+        (n_nodes, n) on the device."""
         f = self.flat
-        vec = self._node_vec[which:which + 1]
+        if vec.shape[-1] != self.ldp or not vec.is_contiguous():
+            full = torch.zeros((f.n_nodes, self.ldp), dtype=torch.float64, device=self.device)
+            full[:, :self.n] = vec[:, :self.n]
+            vec = full
         ml_count = torch.empty(f.n_nodes, dtype=torch.int32, device=self.device)
         ml_prob = torch.empty(f.n_nodes, dtype=torch.float64, device=self.device)
         probs = (torch.zeros((f.n_nodes, self.ldp), dtype=torch.float64, device=self.device)

@@ -82,6 +82,7 @@ class FlatTree:
                     inside = False
                 leaf_code[k] = int(obs) if inside else int(max_chr)
         self.leaf_code = leaf_code
+        self.leaf_names = [nd.name for nd in nodes if not nd.children]
         self.n_leaves = int(np.sum(leaf_code != INTERNAL))
         self.n_leaves_with_data = n_data
 
