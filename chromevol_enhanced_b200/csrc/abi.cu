@@ -74,6 +74,23 @@ __global__ void __launch_bounds__(512) dmma_probe_kernel(int iters, int smem_mod
 #pragma unroll
             for (int i = 0; i < 13; ++i) dmma884(c[i][0], c[i][1], av, bp[i * 32]);
         }
+    } else if (smem_mode >= 200) {
+        // 13 DMMAs + (smem_mode - 200) independent 32-bit integer ops per iteration: do
+        // instructions of other pipes overlap with DMMA issue, or does a DMMA hold the scheduler?
+        const int nint = smem_mode - 200;
+        unsigned x0 = threadIdx.x, x1 = threadIdx.x * 3u, x2 = 7u, x3 = 11u;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 13; ++i) dmma884(c[i][0], c[i][1], av, bv);
+#pragma unroll 1
+            for (int q = 0; q < nint; q += 4) {
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x0) : "r"(x1), "r"(x2));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x1) : "r"(x2), "r"(x3));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x2) : "r"(x3), "r"(x0));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x3) : "r"(x0), "r"(x1));
+            }
+        }
+        if ((x0 ^ x1 ^ x2 ^ x3) == 0x12345u) bv = 2.0;
     } else if (smem_mode >= 100) {
         // 13 DMMAs + (smem_mode - 100) independent DADDs per iteration, register operands: what
         // FP64 ALU work in the epilogue costs the tensor pipe (about 2.5 clocks per DADD)

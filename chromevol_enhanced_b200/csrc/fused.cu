@@ -482,6 +482,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// A warp that finds its barrier not ready sleeps between polls (64 ns, then 256 ns): the warps
+// that wait are the ones AHEAD of the ring, so waking up late costs nothing, while every poll
+// takes an issue slot from a warp that has work.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    __nanosleep(64);
+    while (!mbar_try_wait(bar, parity)) __nanosleep(256);
+}
 
 struct ApplyArgs {
     const double* tc;
@@ -568,11 +576,14 @@ __device__ __forceinline__ void chunk_slots(double (&acc)[F_JT][2], const double
 // variants -- four compare-and-branch pairs per chunk, no per-slot predicates
 __device__ __forceinline__ void chunk_dispatch(const int m, double (&acc)[F_JT][2], const double* Bc,
                                                const double av) {
+    if (m == F_JT) {   // the most frequent count from the third chunk on
+        chunk_slots<13>(acc, Bc, av);
+        return;
+    }
     if (m > 6) {
         if (m > 9) {
             if (m > 11) {
-                if (m > 12) chunk_slots<13>(acc, Bc, av);
-                else chunk_slots<12>(acc, Bc, av);
+                chunk_slots<12>(acc, Bc, av);
             } else {
                 if (m > 10) chunk_slots<11>(acc, Bc, av);
                 else chunk_slots<10>(acc, Bc, av);
@@ -609,7 +620,7 @@ __device__ __forceinline__ void chunk_dispatch(const int m, double (&acc)[F_JT][
 // t ||Q||_1 > theta is written out for the squaring kernel.
 // ONEPASS: n <= 104, a row is a single item (compile-time trip count).
 template <int G, int NW, int MODE, bool ONEPASS>
-__global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? (MODE == APPLY_LEAF ? 3 : 2) : 4))
+__global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4))
     taylor_apply_kernel(ApplyArgs a) {
     constexpr bool LEAF = MODE != APPLY_GENERAL;   // no child vectors in shared memory
     constexpr bool EVAL = MODE == APPLY_EVAL;
@@ -767,8 +778,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? (MODE
                 for (int c = 0; c < ck; ++c) total += (uint32_t)((cnts >> (4 * c)) & 15ull);
                 if (use > 0) {
                     const uint32_t par = (uint32_t)((use - 1) & 1);
-                    while (!mbar_try_wait(&empty[s], par)) {
-                    }
+                    mbar_wait_backoff(&empty[s], par);
                 }
                 mbar_expect_tx(&full[s], total * 256u);
                 double* dst = Bs + (size_t)s * stage_doubles;
@@ -835,7 +845,8 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? (MODE
     const unsigned int row_off = (unsigned)my_child * (unsigned)a.ldp;   // n_nodes * ldp < 2^31
     const double* Aw = As + (size_t)warp * F_KC * 32 + lane;
     const double* Lbase = Ls + (size_t)xw * ldl + 2 * t4;
-    double rs0 = 0.0, rs1 = 0.0, dt0 = 0.0, dt1 = 0.0;
+    double rs0 = -padfix, rs1 = 0.0, dt0 = 0.0, dt1 = 0.0;
+    bool have_prev = false;   // false only while the first item of the CTA is in flight
     double acc[F_JT][2];
 #pragma unroll
     for (int sl = 0; sl < F_JT; ++sl) acc[sl][0] = acc[sl][1] = 0.0;
@@ -853,7 +864,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? (MODE
         if (EVAL) {
             const int jt = nib<SL>(pm_lo, pm_hi);
             const int j = (pass_e * F_JT + jt) * 8 + 2 * t4;
-            if (mine && j < a.ldp)
+            if (mine && have_prev && j < a.ldp)
                 *reinterpret_cast<double2*>(a.X + ((size_t)my_child * n + i_e) * a.ldp + j) =
                     make_double2(p0, p1);
             return;
@@ -878,23 +889,25 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? (MODE
     // The sum over the four lanes of a quad is one DMMA per quantity (partials as the 8x4 A
     // operand times a matrix of ones) instead of a chain of dependent shuffles: the result is only
     // read by the stores, so the warp keeps issuing.
-    auto finish_row = [&](const int i_e) {
+    auto finish_row = [&](const int i_e, const bool store) {
         if (EVAL) return;
         if (CEVB_STUB & 8) {
-            rs0 = rs1 = dt0 = dt1 = 0.0;
+            rs0 = -padfix;
+            rs1 = dt0 = dt1 = 0.0;
             return;
         }
         double r0 = 0.0, r1 = 0.0, d0 = 0.0, d1 = 0.0;
-        dmma884(r0, r1, (rs0 + rs1) - padfix, 1.0);
-        dmma884(d0, d1, dt0 + dt1, 1.0);
-        if (t4 == 0 && mine) {
+        dmma884(r0, r1, rs0 + rs1, 1.0);
+        dmma884(d0, d1, MODE == APPLY_LEAF ? dt0 : dt0 + dt1, 1.0);
+        if (t4 == 0 && mine && store) {
             // vector base: CTA-uniform 64-bit; row offset inside the vector: 32-bit per lane
             const size_t vb = (size_t)b * a.n_nodes * a.ldp;
             const unsigned int o = row_off + (unsigned)i_e;
             (a.w + vb)[o] = d0;
             (a.wr + vb)[o] = r0;
         }
-        rs0 = rs1 = dt0 = dt1 = 0.0;
+        rs0 = -padfix;   // takes the floor of the columns beyond n out of the row sum again
+        rs1 = dt0 = dt1 = 0.0;
     };
 
     // Software pipeline over the items (row, pass): while the first chunk of item q is issued
@@ -902,24 +915,26 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? (MODE
     // and post-processed, so a warp keeps the FP64 pipe fed during its own epilogue.
     int s = 0;
     uint32_t par = 0;
-    int i_prev = 0, pass_prev = 0;
+    // pass_prev starts at the last pass: the epilogue the first item runs on the zero-initialised
+    // accumulators is then closed by a finish_row that stores nothing and resets the sums
+    int i_prev = 0, pass_prev = npass - 1;
     uint32_t pm_prev_lo = 0, pm_prev_hi = 0;
-    bool have_prev = false;
 
     for (int i = i_begin; i < i_end; ++i) {
         for (int pass = 0; pass < npass; ++pass) {
             const uint4 mt = s_meta[(i - i_begin) * npass + pass];
             uint32_t c_lo = mt.z, c_hi = mt.w;
-            if (!(CEVB_STUB & 2)) mbar_wait(&full[s], par);
+            if (!(CEVB_STUB & 2)) mbar_wait_backoff(&full[s], par);
             const double* Bq = Bs + (size_t)s * stage_doubles + lane;
             // chunk 0 is interleaved with the epilogue of the previous item, so its DMMAs are
             // predicated per slot (SL < m(0)); the later chunks branch to the straight-line
             // variant of their slot count
             const int m0 = (int)(c_lo & 15u);
-            if (have_prev) {
+            {
                 // chunk 0 with the epilogue of the previous item between its DMMAs.  Straight-
-                // line variants for 3, 6, 9 or 13 slots (the table rounds m(0) up to one of
-                // them), so no per-slot predicate is needed.
+                // line variants for 0, 3, 6, 9 or 13 slots (the table rounds m(0) up to one of
+                // them), so no per-slot predicate is needed.  The first item of a CTA runs the
+                // epilogue on its zero-initialised accumulators; nothing of that is stored.
                 auto chunk0 = [&](auto Mc) {
                     constexpr int M = decltype(Mc)::value;
                     const double av = Aw[0];
@@ -967,8 +982,6 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? (MODE
                     if (m0 <= 9) chunk0(std::integral_constant<int, 9>{});
                     else chunk0(std::integral_constant<int, 13>{});
                 }
-            } else {
-                chunk_dispatch(m0, acc, Bq, Aw[0]);   // first item: the accumulators are zero
             }
             for (int c = 1; c < wk; ++c) {
                 c_lo = __funnelshift_r(c_lo, c_hi, 4);
@@ -978,14 +991,14 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? (MODE
                 const double* Bc = Bq + (size_t)c * F_CHUNK;
                 if (!(CEVB_STUB & 4)) chunk_dispatch(m, acc, Bc, av);
             }
-            // every shared-memory read of this stage has been consumed by an issued DMMA
-            __syncwarp();
+            // every shared-memory read of this stage has been consumed by an issued DMMA (the
+            // DMMAs are warp-wide, so all lanes' loads are complete)
             if (lane == 0 && !(CEVB_STUB & 2)) mbar_arrive(&empty[s]);
             if (++s == ns) {
                 s = 0;
                 par ^= 1u;
             }
-            if (have_prev && pass_prev == npass - 1) finish_row(i_prev);
+            if (ONEPASS || pass_prev == npass - 1) finish_row(i_prev, have_prev);
             have_prev = true;
             i_prev = i;
             pass_prev = pass;
@@ -1017,7 +1030,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? (MODE
         last(std::integral_constant<int, 10>{});
         last(std::integral_constant<int, 11>{});
         last(std::integral_constant<int, 12>{});
-        finish_row(i_prev);
+        finish_row(i_prev, true);
     }
 }
 

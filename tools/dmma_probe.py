@@ -19,7 +19,9 @@ for mode, name in ((0, "registers"), (1, "LDS per DMMA"), (2, "LDS double-buffer
                    (3, "13 LDS then 13 DMMA"), (4, "LDS.128 per 2 DMMA"),
                    (5, "13 volatile LDS, 13 DMMA"), (6, "volatile, 2 register sets"),
                    (100, "13 DMMA + 0 DADD"), (108, "13 DMMA + 8 DADD"), (128, "13 DMMA + 28 DADD"),
-                   (152, "13 DMMA + 52 DADD")):
+                   (152, "13 DMMA + 52 DADD"), (200, "13 DMMA + 0 LOP3 (loop)"),
+                   (252, "13 DMMA + 52 LOP3"), (304, "13 DMMA + 104 LOP3"),
+                   (408, "13 DMMA + 208 LOP3"), (616, "13 DMMA + 416 LOP3")):
     line = []
     for warps in (1, 2, 4, 8, 12, 16):
         lib.cevb_diag_dmma_probe(sms, warps * 32, 50, mode, _lib.ptr(sink), st)
