@@ -15,6 +15,7 @@ Pipeline per chunk of parameter vectors (one stream, no host synchronisation ins
 from __future__ import annotations
 
 import ctypes
+import gc
 
 import numpy as np
 import torch
@@ -472,8 +473,16 @@ class LikelihoodEngine:
             cur.wait_stream(side)
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                body()
+            # no cyclic-GC pass while the stream is capturing: collecting an old CUDAGraph (or
+            # any object whose finaliser touches the device) inside a capture invalidates it
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(graph):
+                    body()
+            finally:
+                if gc_was_on:
+                    gc.enable()
             entry = (graph, sp, sr, flags)
             self._graphs[key] = entry
         graph, sp, sr, flags = entry

@@ -101,6 +101,13 @@ def transition_probabilities(Q, branch_length, expm=scipy.linalg.expm):
         return np.eye(n)
 
 
+def transition_probabilities_many(args):
+    """(Q, branch lengths) -> list of post-processed matrices; a picklable worker so that tests
+    can spread the oracle's per-branch scipy expm calls over host processes."""
+    Q, lengths = args
+    return [transition_probabilities(Q, float(t)) for t in lengths]
+
+
 def raw_expm(Q, branch_length):
     """Unprocessed expm(Q t) -- the third-party call at AR:151."""
     return scipy.linalg.expm(Q * branch_length)

@@ -106,6 +106,62 @@ def test_product_path_fails_loudly_without_gpu():
     calc = cev.ChromEvolLikelihoodCalculator(t, {"A": 3, "B": 4}, cev.ChromEvolutionModel(10))
     with pytest.raises(CevbError):
         calc.calculate_total_log_likelihood()
+    # device failures are not numerical penalties: the optimiser and model selection raise
+    # instead of reporting a "converged" fit at -1e10 (round-1 advisor finding)
+    opt = cev.ChromEvolOptimizer(t, {"A": 3, "B": 4}, cev.ChromEvolutionModel(10))
+    with pytest.raises(CevbError):
+        opt.objective_function(np.array([0.1, 0.1]), ["gain", "loss"])
+    with pytest.raises(CevbError):
+        opt.optimize_parameters()
+    with pytest.raises(CevbError):
+        cev.calculate_model_selection_criteria(t, {"A": 3, "B": 4}, 10)
+
+
+def test_objective_keeps_numerical_penalties(monkeypatch):
+    """AR:365-371: a numerical exception inside the evaluation is a 1e10 penalty, inf / NaN a 1e9
+    one -- only device errors propagate."""
+    import chromevol_enhanced_b200 as cev
+    t = make_tree("(A:1,B:1);")
+    opt = cev.ChromEvolOptimizer(t, {"A": 3, "B": 4}, cev.ChromEvolutionModel(10))
+    monkeypatch.setattr(opt.calculator, "calculate_total_log_likelihood",
+                        lambda: (_ for _ in ()).throw(FloatingPointError("overflow")))
+    assert opt.objective_function(np.array([0.1, 0.1]), ["gain", "loss"]) == 1e10
+    monkeypatch.setattr(opt.calculator, "calculate_total_log_likelihood", lambda: float("nan"))
+    assert opt.objective_function(np.array([0.1, 0.1]), ["gain", "loss"]) == 1e9
+    monkeypatch.setattr(opt.calculator, "calculate_total_log_likelihood", lambda: -np.inf)
+    assert opt.objective_function(np.array([-3.0, 0.1]), ["gain", "loss"]) == 1e9
+    assert opt.model.params["gain"] == 1e-7                                   # AR:352 clamp
+
+
+def test_max_chromosome_number_limit_is_reported():
+    """The kernels support at most 288 states (CEVB_MAX_N); a larger model says so instead of
+    failing inside a launch."""
+    import chromevol_enhanced_b200 as cev
+    from chromevol_enhanced_b200._lib import CevbError, MAX_STATES
+    header = open(os.path.join(ROOT, "include", "chromevol_b200.h")).read()
+    assert int(re.search(r"#define CEVB_MAX_N (\d+)", header).group(1)) == MAX_STATES
+    t = make_tree("(A:1,B:1);")
+    calc = cev.ChromEvolLikelihoodCalculator(t, {"A": 3, "B": 4}, cev.ChromEvolutionModel(MAX_STATES))
+    with pytest.raises(CevbError, match="at most"):
+        calc.calculate_total_log_likelihood()
+
+
+def test_lazy_memo_behaves_like_a_dict():
+    from chromevol_enhanced_b200.ancestral_reconstruction import _NodeVectors
+    calls = []
+
+    def fill():
+        calls.append(1)
+        return {1: np.arange(3.0), 2: np.ones(3)}
+
+    memo = _NodeVectors(fill, -1.5)
+    assert memo.pending and memo.logl == -1.5 and not calls
+    assert 1 in memo and not memo.pending and len(calls) == 1
+    assert len(memo) == 2 and sorted(memo) == [1, 2] and memo.get(3) is None
+    assert np.array_equal(memo[1], np.arange(3.0)) and len(calls) == 1
+    assert bool(memo) and list(memo.keys()) == [1, 2] and len(list(memo.items())) == 2
+    empty = _NodeVectors(lambda: {}, 0.0)
+    assert not empty and not empty.pending
 
 
 def test_product_package_never_imports_oracle():
