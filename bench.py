@@ -100,8 +100,6 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 def _cpu_worker(args):
     """One host process: faithful oracle evaluations (Q rebuilt per branch like AR:141)."""
-    os.environ["OPENBLAS_NUM_THREADS"] = "1"
-    os.environ["OMP_NUM_THREADS"] = "1"
     newick, counts, rows = args
     from oracle import chromevol_oracle as O
     from chromevol_enhanced_b200 import synthetic
@@ -125,9 +123,22 @@ def cpu_reference_throughput(tree, counts, rows, evals_per_core=1, cores=None):
     chunks = [rows[take[c * evals_per_core:(c + 1) * evals_per_core]] for c in range(cores)]
     newick = tree.write(dist_formatter="%.17g")
     ctx = mp.get_context("spawn")
+    # one BLAS thread per worker process.  The variables are set HERE, before the workers are
+    # spawned: a spawned interpreter imports numpy (and starts its BLAS pool) while it imports
+    # this module, i.e. before any code of the worker function runs.
+    blas_env = ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS")
+    saved = {k: os.environ.get(k) for k in blas_env}
+    os.environ.update({k: "1" for k in blas_env})
     t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(newick, counts, ch) for ch in chunks])
+    try:
+        with ctx.Pool(cores) as pool:
+            res = pool.map(_cpu_worker, [(newick, counts, ch) for ch in chunks])
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     wall = time.perf_counter() - t0
     busy = max(r[0] for r in res)
     lls = [x for r in res for x in r[1]]
@@ -163,6 +174,43 @@ def run_reference_arm(args):
     return 0
 
 
+def ncu_traffic(path):
+    """Mean dram__bytes_read.sum + dram__bytes_write.sum per launch, per kernel family, from the
+    committed ncu CSV of one 512-vector step of the CURRENT kernels (profiles/README.md has the
+    command).  The squaring path's series launches (template MODE 2) are kept apart from the
+    fused apply launches the roofline block describes."""
+    import csv
+    import gzip
+    import re
+    if not os.path.exists(path):
+        return {}
+    with gzip.open(path, "rt") as fh:
+        rows = list(csv.reader(fh))
+    hdr = next((i for i, r in enumerate(rows) if "Kernel Name" in r and "Metric Name" in r), None)
+    if hdr is None:
+        return {}
+    h = rows[hdr]
+    ki, mi, vi, ui, idi = (h.index(x) for x in ("Kernel Name", "Metric Name", "Metric Value", "Metric Unit", "ID"))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = {}
+    for r in rows[hdr + 1:]:
+        if len(r) <= vi or not r[mi].startswith("dram__bytes_"):
+            continue
+        name = r[ki]
+        fam = name.split("<")[0].split("(")[0].replace("void ", "").replace("cevb::", "")
+        if fam == "taylor_apply_kernel":
+            m = re.search(r"taylor_apply_kernel<[^,]*,[^,]*,\s*\(?(?:int\))?\s*(\d+)", name)
+            if m and m.group(1) == "2":
+                fam = "taylor_apply_kernel<EVAL>"
+        try:
+            val = float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
+        except ValueError:
+            continue
+        d = per.setdefault(fam, {})
+        d[r[idi]] = d.get(r[idi], 0.0) + val
+    return {fam: int(sum(d.values()) / len(d)) for fam, d in per.items() if d}
+
+
 def workload_config(args, world):
     return {"workload": f"BASELINE configs[2] per-GPU share: synthetic {N_TAXA}-taxon tree, max count "
                         f"N={MAX_CHR} (n={MAX_CHR + 1} states, 1998 branches), {args.batch} parameter "
@@ -191,8 +239,6 @@ def run_ours(args):
     eng.want_node_vectors = False      # logL only; switched on for the single-vector + states case
     B = rows.shape[0]
     d_rows = torch.as_tensor(rows, device=dev)
-    h_rows = torch.as_tensor(rows).pin_memory()
-    h_out = torch.empty(B, dtype=torch.float64).pin_memory()
 
     def barrier():
         torch.cuda.synchronize()
@@ -200,25 +246,59 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    # One step = enqueue this rank's batch, start the all-gather of its log-likelihoods, then
+    # settle the PREVIOUS step (its flag copy and its gather).  Nothing drains the GPU between
+    # steps; the last step is settled inside the timed region by `drain`.
+    pipe = D.GatherPipeline(B * world, world)
+    state = {"ticket": None, "ll": None}
+
+    def settle():
+        if state["ticket"] is not None:
+            eng.resolve(state["ticket"])
+            state["ticket"] = None
+        got = pipe.collect()
+        if got is not None:
+            state["ll"] = got
+
     def step_resident():
-        ll = eng.log_likelihood(d_rows)
-        if world > 1:
-            ll = D.all_gather_ragged(ll, B * world, world)
-        return ll
+        out, ticket = eng.log_likelihood_deferred(d_rows)
+        prev = state["ticket"]
+        if prev is not None:
+            eng.resolve(prev)
+        got = pipe.collect()
+        if got is not None:
+            state["ll"] = got
+        pipe.submit(out)
+        state["ticket"] = ticket
+        return state["ll"]
+
+    def drain():
+        settle()
+        return state["ll"]
+
+    # the call a user of the drop-in makes for a batch: host array in, host array out
+    # (ChromEvolLikelihoodCalculator.log_likelihood_batch: H2D of the parameter rows, the device
+    # evaluation, D2H of the log-likelihoods, all inside the call)
+    import chromevol_enhanced_b200 as cev
+    model = cev.ChromEvolutionModel(MAX_CHR)
+    calc = cev.ChromEvolLikelihoodCalculator(tree, counts, model)
+    calc.set_root_frequencies(np.ones(MAX_CHR + 1) / (MAX_CHR + 1))
+    calc._device_engine()
+    calc._engine = eng                       # same resident tree and workspace as the timed engine
+    names8 = cev.MODEL_PARAMETER_NAMES
+    rows8 = np.ascontiguousarray(rows[:, :8])
 
     def step_e2e():
-        d = h_rows.to(dev, non_blocking=True)
-        ll = eng.log_likelihood(d)
+        out = calc.log_likelihood_batch(rows8, names8)
         if world > 1:
-            full = D.all_gather_ragged(ll, B * world, world)
-            h_out.copy_(full[rank * B:(rank + 1) * B], non_blocking=False)
-        else:
-            h_out.copy_(ll, non_blocking=False)
-        return h_out
+            full = D.all_gather_ragged(torch.as_tensor(out, device=dev), B * world, world)
+            return full.cpu().numpy()
+        return out
 
     # ---- device-resident timing ("value")
     for _ in range(args.warmup):
         step_resident()
+    drain()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -226,7 +306,8 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        ll = step_resident()
+        step_resident()
+    ll = drain()
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -236,6 +317,7 @@ def run_ours(args):
     # Pade orders / squaring counts the device chose, from one extra untimed step (deterministic)
     eng.keep_info, eng.info_log = True, []
     step_resident()
+    drain()
     barrier()
     eng.keep_info = False
     info_log = eng.info_log
@@ -245,6 +327,7 @@ def run_ours(args):
     barrier()
     for _ in range(args.steps):
         step_resident()
+    drain()
     barrier()
     stage_ms = {}
     for name, a, b in eng.stage_events:
@@ -282,7 +365,8 @@ def run_ours(args):
     barrier()
     t_single = ev0.elapsed_time(ev1) * 1e-3 / reps1
 
-    extras = run_extras(dev, rank, world) if args.extras else None
+    eng.want_node_vectors = False
+    extras = None if args.no_configs else run_other_configs(dev, rank, world, eng, tree, counts)
     if rank != 0:
         D.shutdown()
         return 0
@@ -317,10 +401,7 @@ def run_ours(args):
         best = min(best, e0.elapsed_time(e1) * 1e-3)
     fp64_peak = 2 * 8192 ** 3 / best / 1e12
     del a
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath))
+    traffic = ncu_traffic(os.path.join(ROOT, "profiles", "r02_apply_traffic.csv.gz"))
     peak_src = "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)"
     apply_tf = work["algorithmic_flops"] / apply_s / 1e12 if apply_s > 0 else None
     apply_exec_tf = work["dmma_flops"] / apply_s / 1e12 if apply_s > 0 else None
@@ -392,25 +473,142 @@ def run_ours(args):
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if extras is not None:
-        line["extras"] = extras
+        mu = extras.get("model_selection_unit", {}).get("roofline")
+        if mu and mu.get("achieved"):
+            mu["peak"] = fp64_peak
+            mu["frac"] = mu["achieved"] / fp64_peak
+        if "dropin_objective" in extras:
+            extras["dropin_objective"]["vs_single_vector_ms"] = extras["dropin_objective"]["ms"] / (t_single * 1e3)
+        line["other_configs"] = extras
     print(json.dumps(line))
     D.shutdown()
     return 0
 
 
-def run_extras(dev, rank, world):
-    """Side measurements for the other BASELINE configs (not the headline metric):
-    configs[4] stochastic mapping replicates/s on the 1,000-taxon tree (replicates sharded over
-    ranks, disjoint Philox counters) and configs[3]'s building block, one log-likelihood
-    evaluation on a 10,000-taxon tree with N=256."""
+def _shipped_data():
+    """The reference's shipped tree + counts (data/pruned_phylogeny.nwk, data/chromosome_counts.csv)
+    as committed with the golden fixtures (tests/golden/golden.json)."""
+    with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as fh:
+        meta = json.load(fh)
+    return meta["shipped_newick"], dict(meta["shipped_counts"])
+
+
+def run_other_configs(dev, rank, world, eng2, tree2, counts2):
+    """The other BASELINE configs, every run (they add a few seconds):
+    configs[0] shipped data, --use_chromevol --optimize_params through the drop-in;
+    configs[1/2] the reference-shaped objective call, the 9-point finite-difference step sharded
+    over the ranks, and the full 4,096-vector batch on one GPU;
+    configs[3] one evaluation on a 10,000-taxon tree with N=256, with its own roofline block;
+    configs[4] 1e6 stochastic-mapping replicates sharded over the ranks."""
     import torch
-    from chromevol_enhanced_b200 import mapper, synthetic
+    import chromevol_enhanced_b200 as cev
+    from chromevol_enhanced_b200 import accounting, mapper, synthetic
     from chromevol_enhanced_b200 import distributed as D
     from chromevol_enhanced_b200.engine import LikelihoodEngine
     from chromevol_enhanced_b200.flatten import FlatTree
+    from chromevol_enhanced_b200.newick import Tree
     out = {}
-    tree = synthetic.random_tree(N_TAXA, seed=TREE_SEED)
-    flat = FlatTree(tree, {}, MAX_CHR)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+
+    # ---- configs[0]: shipped data through the drop-in classes (rank 0; 73 branches, N=35)
+    if rank == 0:
+        newick, counts = _shipped_data()
+        res0 = {}
+        for label, batched in (("sequential_gradient", False), ("batched_gradient", True)):
+            tree = Tree(newick, format=1)
+            model = cev.ChromEvolutionModel(35)
+            calc = cev.ChromEvolLikelihoodCalculator(tree, counts, model)
+            calc.set_root_frequencies(np.ones(36) / 36)
+            opt = cev.ChromEvolOptimizer(tree, counts, model)
+            opt.calculator = calc
+            opt.batched_gradient = batched
+            calc.calculate_total_log_likelihood()          # flatten + first graph capture: untimed
+            calc.likelihoods = {}
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = opt.optimize_parameters()
+            calc.likelihoods = {}
+            ll = calc.calculate_total_log_likelihood()
+            calc.ancestral_state_reconstruction()
+            torch.cuda.synchronize()
+            res0[label] = {"seconds": time.perf_counter() - t0, "nfev": int(r.nfev) if r else None,
+                           "nit": int(r.nit) if r else None, "logL": float(ll)}
+        res0["workload"] = ("BASELINE configs[0]: shipped pruned_phylogeny.nwk + chromosome_counts.csv, N=35, "
+                            "optimize_parameters (L-BFGS-B from the defaults) + final logL + ancestral states "
+                            "through ChromEvolOptimizer / ChromEvolLikelihoodCalculator")
+        res0["reference_seconds"] = 14.4
+        res0["reference_note"] = ("the unmodified reference on the survey container's CPU (SURVEY.md section "
+                                  "8(d): 504 evaluations, logL -55.1204); not re-measured on this box")
+        out["shipped_optimise"] = res0
+
+    # ---- the reference-shaped objective call at configs[1] (1,000 taxa, N=100), rank 0
+    if rank == 0:
+        model = cev.ChromEvolutionModel(MAX_CHR)
+        opt = cev.ChromEvolOptimizer(tree2, counts2, model)
+        opt.calculator.set_root_frequencies(np.ones(MAX_CHR + 1) / (MAX_CHR + 1))
+        names = cev.ChromEvolOptimizer.DEFAULT_PARAM_NAMES
+        x = np.array([model.params[nm] for nm in names])
+        for _ in range(3):
+            opt.objective_function(x, names)
+        torch.cuda.synchronize()
+        reps = 20
+        t0 = time.perf_counter()
+        for k in range(reps):
+            x[0] = 0.1 + 1e-4 * k
+            f = opt.objective_function(x, names)
+        wall = (time.perf_counter() - t0) / reps
+        out["dropin_objective"] = {"workload": "ChromEvolOptimizer.objective_function (AR:341-371), 1,000 taxa, N=100: "
+                                               "one scalar back per call, node vectors stay on the device",
+                                   "ms": wall * 1e3, "neg_logL": float(f)}
+
+    # ---- the 9-point finite-difference step of one L-BFGS-B gradient, sharded over the ranks
+    rows9 = np.tile(synthetic.default_param_row(), (9, 1))
+    for k in range(8):
+        rows9[k + 1, k] += 1e-8
+    d9 = torch.as_tensor(rows9, device=dev)
+    lo, hi = D.shard_bounds(9, rank, world)
+
+    def fd_step():
+        local = eng2.log_likelihood(d9[lo:hi]) if hi > lo else torch.zeros(0, dtype=torch.float64, device=dev)
+        return D.all_gather_ragged(local, 9, world)
+
+    for _ in range(3):
+        fd_step()
+    sync()
+    e0.record()
+    for _ in range(10):
+        g = fd_step()
+    e1.record()
+    sync()
+    t_fd = D.max_across_ranks(e0.elapsed_time(e1) * 1e-3 / 10, dev)
+    out["fd_gradient_step"] = {"workload": "BASELINE configs[1/2]: the 9 evaluations of one forward-difference "
+                                           "gradient (1,000 taxa, N=100) split over the ranks + all-gather",
+                               "ms": t_fd * 1e3, "evals_per_s": 9 / t_fd, "logL0": float(g[0])}
+
+    # ---- the full configs[2] batch (4,096 vectors) on ONE GPU (rank 0 only: a strong-scaling anchor)
+    if rank == 0:
+        rows4k = synthetic.random_param_rows(4096, seed=PARAM_SEED, linear='positive')
+        d4k = torch.as_tensor(rows4k, device=dev)
+        eng2.log_likelihood(d4k)
+        torch.cuda.synchronize()
+        e0.record()
+        eng2.log_likelihood(d4k)
+        e1.record()
+        torch.cuda.synchronize()
+        t4k = e0.elapsed_time(e1) * 1e-3
+        out["full_batch_one_gpu"] = {"workload": "BASELINE configs[2]: all 4,096 parameter vectors of one optimiser "
+                                                 "step on a single GPU", "ms": t4k * 1e3, "evals_per_s": 4096 / t4k,
+                                     "chunks": eng2.n_chunks}
+        del d4k
+    sync()
+
+    # ---- configs[4]: 1e6 stochastic-mapping replicates, sharded over the ranks
+    flat = FlatTree(tree2, {}, MAX_CHR)
     root = np.zeros(MAX_CHR + 1)
     root[20] = 1.0
     reps = 1_000_000
@@ -418,44 +616,74 @@ def run_extras(dev, rank, world):
     row = synthetic.default_param_row()
     mapper.simulate(flat, row, MAX_CHR + 1, root, reps, 7, rep_begin=lo, rep_end=min(hi, lo + 4096),
                     return_device=True)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
     e0.record()
     hist, sums, n_events = mapper.simulate(flat, row, MAX_CHR + 1, root, reps, 7, rep_begin=lo, rep_end=hi,
                                            return_device=True)
+    if world > 1:
+        D.sum_across_ranks(hist)
     e1.record()
-    torch.cuda.synchronize()
+    sync()
     t = D.max_across_ranks(e0.elapsed_time(e1) * 1e-3, dev)
     ev = D.sum_across_ranks(n_events.to(torch.float64)).item() if world > 1 else float(n_events.item())
-    out["stochastic_mapping"] = {"workload": "BASELINE configs[4]: 1e6 replicates, 1,000-taxon tree, N=100, default rates",
+    out["stochastic_mapping"] = {"workload": "BASELINE configs[4]: 1e6 replicates of the 1,000-taxon tree (N=100, default "
+                                             "rates), replicates sharded over the ranks, histograms summed (NCCL)",
                                  "replicates_per_s": reps / t, "events_per_s": ev / t,
                                  "branch_visits_per_s": reps * flat.n_branches / t, "seconds": t}
-    # configs[3] building block: one evaluation (and a 9-point finite-difference batch) at N=256
-    big = synthetic.random_tree(10_000, seed=11)
-    rng = np.random.default_rng(12)      # tip counts: seeded integers (simulating them down the
-    counts = {leaf.name: int(c) for leaf, c in      # tree would cost 20k scipy expm calls at n=257)
-              zip(big.get_leaves(), rng.integers(25, 60, size=10_000))}
-    fl = FlatTree(big, counts, 256)
-    eng = LikelihoodEngine(fl, device=dev, max_workspace_bytes=64 << 30)
-    eng.want_node_vectors = False
-    res = {}
-    for nb in (1, 9):
-        rows = np.tile(synthetic.default_param_row(), (nb, 1))
-        rows[:, 0] *= 1.0 + 1e-3 * np.arange(nb)
-        d = torch.as_tensor(rows, device=dev)
+
+    # ---- configs[3] building block: one evaluation (and the 9-point gradient batch) on a
+    # 10,000-taxon tree with N=256, rank 0, with the roofline of its own apply launches
+    if rank == 0:
+        big = synthetic.random_tree(10_000, seed=11)
+        bcounts = synthetic.simulate_tip_counts_fast(big, 256, seed=12, root_state=40)
+        fl = FlatTree(big, bcounts, 256)
+        eng = LikelihoodEngine(fl, device=dev, max_workspace_bytes=64 << 30)
+        eng.want_node_vectors = False
+        res = {}
+        for nb in (1, 9):
+            rows = np.tile(synthetic.default_param_row(), (nb, 1))
+            rows[:, 0] *= 1.0 + 1e-3 * np.arange(nb)
+            d = torch.as_tensor(rows, device=dev)
+            eng.log_likelihood(d)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                ll = eng.log_likelihood(d)
+            e1.record()
+            torch.cuda.synchronize()
+            res[f"batch_{nb}_ms"] = e0.elapsed_time(e1) / 3
+        # stage times + series accounting of the 9-vector batch
+        eng.keep_info, eng.info_log = True, []
+        eng.graph_max_batch = 0                     # eager launches so that stage events can be placed
         eng.log_likelihood(d)
         torch.cuda.synchronize()
-        e0.record()
-        for _ in range(3):
-            ll = eng.log_likelihood(d)
-        e1.record()
+        eng.keep_info = False
+        norms = np.concatenate([x[2] for x in eng.info_log])
+        work = accounting.fused_work(fl, norms[:, 12], norms[:, 11])
+        eng.stage_events = []
+        eng.log_likelihood(d)
         torch.cuda.synchronize()
-        res[f"batch_{nb}_ms"] = e0.elapsed_time(e1) / 3
-    res["logL"] = float(ll[0])
-    res["workload"] = ("BASELINE configs[3] building block: 10,000-taxon tree, N=256 (n=257, 19,998 branches), "
-                       "default rates; one evaluation and the 9-point gradient batch of one L-BFGS-B step")
-    res["squaring_path"] = eng.squaring
-    out["model_selection_unit"] = res
+        st = {}
+        for name, a, b in eng.stage_events:
+            st[name] = st.get(name, 0.0) + a.elapsed_time(b)
+        eng.stage_events = None
+        apply_s = st.get("apply", 0.0) * 1e-3
+        res["stage_ms"] = st
+        res["logL"] = float(ll[0])
+        res["rescales"] = int(eng.rescale_counts[0])
+        res["squaring_path"] = eng.squaring
+        res["workload"] = ("BASELINE configs[3] building block: 10,000-taxon tree, N=256 (n=257, 19,998 branches), "
+                           "default rates; one evaluation and the 9-point gradient batch of one L-BFGS-B step "
+                           "(model-selection candidates are independent optimiser runs, sharded by candidate)")
+        res["roofline"] = {"kernel": "taylor_apply_kernel (n=257: three passes of 13 tiles per row)",
+                           "bound": "tensor", "unit": "TFLOP/s",
+                           "achieved": work["algorithmic_flops"] / apply_s / 1e12 if apply_s > 0 else None,
+                           "executed_dmma_tflops": work["dmma_flops"] / apply_s / 1e12 if apply_s > 0 else None,
+                           "fused_pairs": work["fused_pairs"], "mean_series_terms": work["mean_ncoef"],
+                           "note": "9-vector batch, single stream, CUDA events per stage; peak = the DGEMM "
+                                   "figure of the main roofline block"}
+        out["model_selection_unit"] = res
+    sync()
     return out
 
 
@@ -468,9 +696,10 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="parameter vectors per GPU per step")
     ap.add_argument("--workspace-gb", type=int, default=48)
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--extras", action="store_true",
-                    help="also time the stochastic mapper (configs[4]) and an N=256 / 10,000-taxon "
-                         "evaluation (configs[3]); adds about a minute")
+    ap.add_argument("--extras", action="store_true", help="(default now; kept for old command lines)")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the other BASELINE configs (shipped-data optimise, N=256 / 10,000 taxa, "
+                         "stochastic mapping, finite-difference step, 4,096-vector batch)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: libraries that print to file descriptor 1 (NCCL's
     # version banner on rank 0) are sent to stderr, and the JSON line goes to the real stdout

@@ -61,8 +61,50 @@ def sharded_log_likelihood(evaluate, params_rows):
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     lo, hi = shard_bounds(params_rows.shape[0], rank, world)
-    local = evaluate(params_rows[lo:hi]) if hi > lo else torch.zeros(0, dtype=torch.float64)
+    if hi > lo:
+        local = evaluate(params_rows[lo:hi])
+    else:
+        # an empty shard (fewer vectors than ranks) still joins the collective, on the device
+        # the backend works on
+        on_gpu = dist.is_initialized() and dist.get_backend() == "nccl"
+        local = torch.zeros(0, dtype=torch.float64,
+                            device=torch.device("cuda", torch.cuda.current_device()) if on_gpu else "cpu")
     return all_gather_ragged(local, params_rows.shape[0], world)
+
+
+class GatherPipeline:
+    """All-gather of per-rank log-likelihood shards that overlaps the next step: `submit` starts
+    the collective (async on NCCL's stream, ordered after the producing kernels) and returns at
+    once; `collect` hands out the gathered vector of the PREVIOUS submit.  One collective is in
+    flight at a time, so a step costs its own kernels, not kernels + collective latency."""
+
+    def __init__(self, total, world=None):
+        self.total = int(total)
+        self.world = (dist.get_world_size() if dist.is_initialized() else 1) if world is None else world
+        self.sizes = [shard_bounds(self.total, r, self.world)[1] - shard_bounds(self.total, r, self.world)[0]
+                      for r in range(self.world)]
+        self.width = max(self.sizes) if self.sizes else 0
+        self._pending = None
+
+    def submit(self, local):
+        if self.world == 1:
+            self._pending = (None, local)
+            return
+        padded = torch.zeros(self.width, dtype=local.dtype, device=local.device)
+        padded[:local.numel()] = local
+        out = torch.empty(self.world * self.width, dtype=local.dtype, device=local.device)
+        work = dist.all_gather_into_tensor(out, padded, async_op=True)
+        self._pending = (work, out)
+
+    def collect(self):
+        if self._pending is None:
+            return None
+        work, out = self._pending
+        self._pending = None
+        if work is None:
+            return out
+        work.wait()               # the current stream waits for the collective; the host does not
+        return torch.cat([out[r * self.width:r * self.width + self.sizes[r]] for r in range(self.world)])
 
 
 def chromevol_model_configurations():

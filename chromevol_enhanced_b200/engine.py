@@ -443,6 +443,33 @@ class LikelihoodEngine:
         self.last_batch = B
         return out
 
+    # ------------------------------------------------------------------ pipelined callers
+    def log_likelihood_deferred(self, params, root_freq=None):
+        """Enqueue one batch WITHOUT reading the overflow / growth flags back: returns
+        (logL tensor, ticket).  The flags travel to pinned host memory behind the kernels;
+        ``resolve(ticket)`` -- typically called after the NEXT batch has been enqueued -- waits
+        for that copy only, and redoes the batch synchronously in the (rare) flagged case.  A
+        caller that pipelines like this never drains the GPU between optimiser steps; the
+        multi-GPU bench gathers the log-likelihoods of step k while step k+1 computes."""
+        d_params = params if torch.is_tensor(params) else torch.as_tensor(
+            np.ascontiguousarray(params, dtype=np.float64), device=self.device)
+        out = self.log_likelihood(d_params, root_freq=root_freq, check_growth=False)
+        flags = torch.stack([self._growth_flag, self._overflow_flag])
+        host = torch.empty(2, dtype=torch.bool).pin_memory()
+        host.copy_(flags, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream())
+        return out, (host, done, d_params, root_freq, out)
+
+    def resolve(self, ticket):
+        """Finish a deferred batch: returns True when the enqueued result stands."""
+        host, done, d_params, root_freq, out = ticket
+        done.synchronize()
+        if not bool(host[0]) and not bool(host[1]):
+            return True
+        out.copy_(self.log_likelihood(d_params, root_freq=root_freq))     # checked, synchronous
+        return False
+
     def _graph_log_likelihood(self, d_params, d_root):
         """Small batch through a captured CUDA graph; None when the captured run has to be redone
         eagerly (work-list overflow)."""

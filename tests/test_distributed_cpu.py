@@ -37,6 +37,18 @@ def _worker(rank, world, port, total, out_dir):
         return -(r[:, 0] * 2.0 + r[:, 7])
 
     full = D.sharded_log_likelihood(fake_eval, rows)
+    # pipelined gather: collect() returns the vector of the PREVIOUS submit
+    lo, hi = D.shard_bounds(total, rank, world)
+    pipe = D.GatherPipeline(total, world)
+    assert pipe.collect() is None
+    pipe.submit(fake_eval(rows[lo:hi]))
+    first = pipe.collect()
+    pipe.submit(2.0 * fake_eval(rows[lo:hi]))
+    second = pipe.collect()
+    assert torch.equal(first, full) and torch.equal(second, 2.0 * full) and pipe.collect() is None
+    # fewer vectors than ranks: the empty shard still joins the collective
+    tiny = D.sharded_log_likelihood(fake_eval, rows[:1])
+    assert tiny.shape == (1,) and tiny[0] == full[0]
     hist = torch.full((4, 8), rank + 1, dtype=torch.int64)
     D.sum_across_ranks(hist)
     mx = D.max_across_ranks(10.0 + rank, torch.device("cpu"))
