@@ -88,11 +88,18 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("CEVB_LIB") or _build.LIB_PATH     # CEVB_LIB: development builds only
-    if not os.path.exists(path):
-        if not build_if_missing:
-            raise CevbError(f"CUDA extension not built: {path}")
-        _build.build()
+    path = os.environ.get("CEVB_LIB")                        # CEVB_LIB: development builds only
+    if not path:
+        path = _build.LIB_PATH
+        if _build.needs_build():
+            # missing, or built from other sources than the tree holds (an edited kernel, a
+            # pulled commit): a stale binary is never used silently
+            if not build_if_missing and not os.path.exists(path):
+                raise CevbError(f"CUDA extension not built: {path}")
+            try:
+                _build.build()
+            except RuntimeError as e:
+                raise CevbError(f"CUDA extension is missing or stale and cannot be rebuilt: {e}") from e
     lib = ctypes.CDLL(path)
     for name, (restype, argtypes) in _PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol

@@ -529,10 +529,9 @@ class LikelihoodEngine:
         above a child uses ``model.branch_params.get(id(child), model.params)``).
 
         param_rows: (S, 9) distinct parameter sets; node_set[k]: the set used on the branch above
-        node k (the root's entry is ignored).  Every set's transition matrices are formed for
-        every branch length (S x n_t matrices, the scipy-algorithm kernels), the matrix of each
-        (set, length) pair in use is gathered, and ONE pruning pass runs over the gathered
-        matrices.  Materialised path only.  Returns the log-likelihood as a 0-d CUDA tensor;
+        node k (the root's entry is ignored).  The transition matrix of every (set, length) pair
+        in use is formed by the scipy-algorithm kernels (work-list form: at most one matrix per
+        branch, as in the reference) and ONE pruning pass runs over them.  Materialised path only.  Returns the log-likelihood as a 0-d CUDA tensor;
         node vectors / ancestral states of the evaluation are read with which=0."""
         if self.path != "materialised":
             raise _lib.CevbError("branch-specific parameter sets need path='materialised'")
@@ -544,26 +543,45 @@ class LikelihoodEngine:
             raise ValueError("node_set must hold one parameter-set index per node")
         d_root = root_freq if torch.is_tensor(root_freq) else self.root_freq_tensor(root_freq)
         self.eval_token += 1
-        self._ensure(S)
-        ws = self._ws
-        ws.params[:S].copy_(torch.as_tensor(rows, device=self.device))
         non_root = np.arange(f.n_nodes) != f.root
         pair = node_set * f.n_t + f.branch_of.astype(np.int64)       # (set, branch-length) index
         uniq, inverse = np.unique(pair[non_root], return_inverse=True)
         branch_of = np.zeros(f.n_nodes, dtype=np.int32)
         branch_of[non_root] = inverse.astype(np.int32)
+        U = int(uniq.size)
+        # Only the (set, length) pairs in use are computed -- at most one matrix per branch, like
+        # the reference (AR:230-237) -- through the work-list form of the expm kernels: position q
+        # of the list computes pair uniq[q] into P slot q, so P is already in pruning order.
+        ws = self._het_workspace(S, U)
+        ws.params[:S].copy_(torch.as_tensor(rows, device=self.device))
         d_branch_of = torch.as_tensor(branch_of, device=self.device)
-        d_uniq = torch.as_tensor(uniq, device=self.device)
+        ws.worklist[:U].copy_(torch.as_tensor(uniq.astype(np.int32), device=self.device))
+        ws.work_count.zero_()
+        ws.work_count[0] = U
+        lib, st = self.lib, _stream_ptr()
+        _lib.check(lib.cevb_build_q(_lib.ptr(ws.params), S, self.n, _lib.ptr(ws.pw), st), "cevb_build_q")
+        _lib.check(lib.cevb_expm_prepare(_lib.ptr(ws.pw), S, self.n, _lib.ptr(ws.norms),
+                                         _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt), st), "cevb_expm_prepare")
         full_pivot = 0
         while True:
-            self._transition_matrices(ws, S, full_pivot)
-            if full_pivot or not bool((((ws.info[:S] >> 16) & INFO_GROWTH) != 0).any().item()):
+            _lib.check(lib.cevb_expm_branches_list(
+                _lib.ptr(ws.pw), _lib.ptr(ws.norms), _lib.ptr(ws.csc), _lib.ptr(ws.csc_cnt),
+                _lib.ptr(self.d_t), S, f.n_t, self.n, _lib.ptr(ws.P), _lib.ptr(ws.info),
+                _lib.ptr(ws.scratch), _lib.ptr(ws.counter), full_pivot, _lib.ptr(ws.worklist),
+                _lib.ptr(ws.work_count), U, st), "cevb_expm_branches_list")
+            flagged = ws.info.reshape(-1).index_select(0, ws.worklist[:U].to(torch.int64))
+            if full_pivot or not bool((((flagged >> 16) & INFO_GROWTH) != 0).any().item()):
                 break
             self.repivot_events += 1     # element-growth monitor tripped: full pivoting
             full_pivot = 1
-        P_het = ws.P[:S].reshape(S * f.n_t, self.n, self.ldp).index_select(0, d_uniq).contiguous()
+        if self._node_vec is None:
+            # only the vectors of one evaluation: not the S x n_t matrices _ensure() would size
+            f64 = dict(dtype=torch.float64, device=self.device)
+            self._node_vec = torch.empty((1, f.n_nodes, self.ldp), **f64)
+            self._logl = torch.empty(1, **f64)
+            self._rescales = torch.zeros(1, dtype=torch.int32, device=self.device)
         _lib.check(self.lib.cevb_prune(
-            _lib.ptr(P_het), 1, int(uniq.size), self.n, f.n_nodes, f.root,
+            _lib.ptr(ws.P), 1, U, self.n, f.n_nodes, f.root,
             _lib.ptr(self.d_level_nodes),
             self.h_level_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), f.n_levels,
             _lib.ptr(self.d_child_off), _lib.ptr(self.d_child_idx), _lib.ptr(d_branch_of),
@@ -572,6 +590,18 @@ class LikelihoodEngine:
         self.rescale_counts = self._rescales[:1].clone()
         self.last_batch = 1
         return self._logl[0].clone()
+
+    def _het_workspace(self, S, U):
+        """Buffers for S parameter sets and U (set, length) pairs in use: powers and norms per
+        set, one P slot per pair (the materialised engine's own workspace is sized for every
+        set x length combination and is not touched)."""
+        ws = getattr(self, "_het_ws", None)
+        if ws is None or ws.cap < S or ws.p_slots < U:
+            ws = ExpmWorkspace(self.n, self.flat.n_t, max(S, 1), self.device, p_slots=max(U, 1))
+            ws.worklist = torch.empty(max(U, 1), dtype=torch.int32, device=self.device)
+            ws.work_count = torch.zeros(16, dtype=torch.int32, device=self.device)
+            self._het_ws = ws
+        return ws
 
     def node_vectors(self, which=0):
         """Conditional-likelihood vectors (n_nodes, n) of vector `which` of the last chunk."""

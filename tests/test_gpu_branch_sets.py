@@ -131,3 +131,35 @@ def test_too_many_parameter_sets_for_the_mapper_is_an_error():
                           node_set=np.arange(flat.n_nodes) % 6)
     assert res.n_events > 0 and not res.overflowed()
     torch.cuda.synchronize()
+
+
+def test_one_parameter_set_per_branch_costs_one_matrix_per_branch():
+    """Every branch with its own parameter set (S = number of branches): the device path forms
+    one transition matrix per branch like the reference (AR:230-237), not S x n_t of them
+    (round-1 advisor finding: that was 300 GB at 1,000 taxa)."""
+    from chromevol_enhanced_b200 import synthetic
+    from chromevol_enhanced_b200.ancestral_reconstruction import (ChromEvolLikelihoodCalculator,
+                                                                  ChromEvolutionModel)
+    N, taxa = 60, 150
+    tree = synthetic.random_tree(taxa, seed=21)
+    counts = synthetic.simulate_tip_counts(tree, N, seed=22)
+    model = ChromEvolutionModel(N)
+    overrides = {}
+    rng = np.random.default_rng(3)
+    for nd in tree.traverse():
+        if nd.is_root():
+            continue
+        kw = {"gain": float(rng.uniform(0.05, 2.0)), "loss": float(rng.uniform(0.05, 2.0))}
+        model.set_branch_parameters(id(nd), **kw)
+        overrides[id(nd)] = O.default_params(**kw)
+    calc = ChromEvolLikelihoodCalculator(tree, counts, model)
+    calc.set_root_frequencies(np.ones(N + 1) / (N + 1))
+    rows, node_set = calc.branch_parameter_sets()
+    n_branches = 2 * taxa - 2
+    assert rows.shape[0] == n_branches + 1
+    ll = calc.calculate_total_log_likelihood()
+    ref, _, _ = O.log_likelihood(tree, counts, N, O.default_params(), np.ones(N + 1) / (N + 1),
+                                 branch_params=overrides)
+    assert ll == pytest.approx(ref, rel=1e-9)
+    ws = calc._het_engine._het_ws
+    assert ws.P.shape[0] == n_branches          # one slot per (set, length) pair in use
