@@ -353,14 +353,16 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
                 s_counts[r][p] |= (unsigned long long)cnt << (4 * c);
             }
             __syncthreads();
-            // write-out in slot order; slots beyond the active prefix hold zeros at this chunk
+            // write-out in slot order.  Only the slot prefix the kernels copy is written: the
+            // active slots and, for chunk 0, the zero slots its count is rounded up to.
             for (int r = 0; r < TCR; ++r) {
                 if (i0 + r >= n) break;
                 for (int p = 0; p < npass; ++p) {
                     const int ns = s_nslot[r][p];
+                    const int nw = (int)((s_counts[r][p] >> (4 * c)) & 15ull);
                     double2* dst = reinterpret_cast<double2*>(
                         tcb + ((size_t)((i0 + r) * npass + p) * F_KC + c) * F_CHUNK);
-                    for (int x = tid; x < F_JT * 16; x += 128) {
+                    for (int x = tid; x < nw * 16; x += 128) {
                         const int sl = x >> 4, rem = x & 15;   // rem = column * 2 + half
                         double2 v = make_double2(0.0, 0.0);
                         if (sl < ns) {
@@ -645,6 +647,15 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     double* Ls = As + (size_t)(EB / 8) * F_KC * 32;                           // [EB][ldl] (not LEAF)
     double* Bs = Ls + (LEAF ? 0 : (size_t)EB * ldl);                          // ring of item tiles
 
+    if (EVAL) {
+        // The launch covers every (vector, branch length) pair, but only the few pairs whose
+        // series needs squarings have work here.  The list is ordered by decreasing length and
+        // "needs squarings" is monotone in the length, so a CTA whose FIRST item does not need
+        // them has nothing to do: it leaves before the prologue (one broadcast load).
+        if (e0 >= a.n_items) return;
+        const int pn0 = a.plan_nc[(size_t)b * a.E + a.items[e0]];
+        if ((pn0 >> 8) != 2) return;
+    }
     const double* tcb = a.tc + (size_t)b * taylor_vec_doubles(n);
     {
         // meta data of this CTA's items: (perm | inv, counts).  The leaf variant selects one
