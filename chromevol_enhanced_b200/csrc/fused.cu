@@ -566,44 +566,45 @@ __device__ __forceinline__ void dmma884_if(double& c0, double& c1, double a, dou
 // and only then the M DMMAs (an LDS placed right before its DMMA, or right after a DMMA that
 // still has to read the same register, serialises the warp on the shared-memory latency -- see
 // tools/dmma_probe.py; the compiler barriers keep the two groups apart).
-template <int M>
+template <int M, bool DIRECT>
 __device__ __forceinline__ void chunk_slots(double (&acc)[F_JT][2], const double* Bc, const double av) {
     double bv[M > 0 ? M : 1];
 #pragma unroll
-    for (int sl = 0; sl < M; ++sl) bv[sl] = Bc[sl * 32];
+    for (int sl = 0; sl < M; ++sl) bv[sl] = DIRECT ? __ldg(Bc + sl * 32) : Bc[sl * 32];
 #pragma unroll
     for (int sl = 0; sl < M; ++sl) dmma884(acc[sl][0], acc[sl][1], av, bv[sl]);
 }
 // the same for a run-time slot count m (warp-uniform): a compare tree over the 13 straight-line
 // variants -- four compare-and-branch pairs per chunk, no per-slot predicates
+template <bool DIRECT>
 __device__ __forceinline__ void chunk_dispatch(const int m, double (&acc)[F_JT][2], const double* Bc,
                                                const double av) {
     if (m == F_JT) {   // the most frequent count from the third chunk on
-        chunk_slots<13>(acc, Bc, av);
+        chunk_slots<13, DIRECT>(acc, Bc, av);
         return;
     }
     if (m > 6) {
         if (m > 9) {
             if (m > 11) {
-                chunk_slots<12>(acc, Bc, av);
+                chunk_slots<12, DIRECT>(acc, Bc, av);
             } else {
-                if (m > 10) chunk_slots<11>(acc, Bc, av);
-                else chunk_slots<10>(acc, Bc, av);
+                if (m > 10) chunk_slots<11, DIRECT>(acc, Bc, av);
+                else chunk_slots<10, DIRECT>(acc, Bc, av);
             }
         } else {
-            if (m > 8) chunk_slots<9>(acc, Bc, av);
-            else if (m > 7) chunk_slots<8>(acc, Bc, av);
-            else chunk_slots<7>(acc, Bc, av);
+            if (m > 8) chunk_slots<9, DIRECT>(acc, Bc, av);
+            else if (m > 7) chunk_slots<8, DIRECT>(acc, Bc, av);
+            else chunk_slots<7, DIRECT>(acc, Bc, av);
         }
     } else {
         if (m > 3) {
-            if (m > 5) chunk_slots<6>(acc, Bc, av);
-            else if (m > 4) chunk_slots<5>(acc, Bc, av);
-            else chunk_slots<4>(acc, Bc, av);
+            if (m > 5) chunk_slots<6, DIRECT>(acc, Bc, av);
+            else if (m > 4) chunk_slots<5, DIRECT>(acc, Bc, av);
+            else chunk_slots<4, DIRECT>(acc, Bc, av);
         } else {
-            if (m > 2) chunk_slots<3>(acc, Bc, av);
-            else if (m > 1) chunk_slots<2>(acc, Bc, av);
-            else if (m > 0) chunk_slots<1>(acc, Bc, av);
+            if (m > 2) chunk_slots<3, DIRECT>(acc, Bc, av);
+            else if (m > 1) chunk_slots<2, DIRECT>(acc, Bc, av);
+            else if (m > 0) chunk_slots<1, DIRECT>(acc, Bc, av);
         }
     }
 }
@@ -621,8 +622,16 @@ __device__ __forceinline__ void chunk_dispatch(const int m, double (&acc)[F_JT][
 // epilogue arithmetic at all -- the series value at the scaled time t 2^-s of every pair with
 // t ||Q||_1 > theta is written out for the squaring kernel.
 // ONEPASS: n <= 104, a row is a single item (compile-time trip count).
-template <int G, int NW, int MODE, bool ONEPASS>
-__global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4))
+// DIRECT: the small launches of the upper tree levels (a few 8-branch groups per vector).  With
+// one or three consumer warps per CTA and a 40 KB ring per CTA, an SM holds about one consumer
+// warp per scheduler and every latency of that warp is exposed (measured: 2.5 us per row
+// against 0.5 us of issue time).  The DIRECT variant has no ring, no producer and no mbarriers:
+// a warp loads the B fragments of a chunk straight from the table in global memory (the slot
+// layout is lane-contiguous, so a fragment load is one coalesced 256-byte request), which
+// leaves room for 16 consumer warps per SM that hide each other's load latency.
+template <int G, int NW, int MODE, bool ONEPASS, bool DIRECT = false>
+__global__ void __launch_bounds__(32 * (NW + (DIRECT ? 0 : 1)),
+                                  DIRECT ? 16 / NW : (NW >= 15 ? 1 : (NW == 7 ? 2 : 4)))
     taylor_apply_kernel(ApplyArgs a) {
     constexpr bool LEAF = MODE != APPLY_GENERAL;   // no child vectors in shared memory
     constexpr bool EVAL = MODE == APPLY_EVAL;
@@ -733,14 +742,16 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
     int ns = a.stage_doubles_cap / stage_doubles;
     if (ns > F_MAXSTAGE) ns = F_MAXSTAGE;
 
-    if (tid == 0) {
-        for (int s = 0; s < ns; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], __popc(active));
+    if (!DIRECT) {
+        if (tid == 0) {
+            for (int s = 0; s < ns; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], __popc(active));
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();   // barriers initialised
     }
-    __syncthreads();   // barriers initialised
 
     if (warp != NW && !LEAF) {
         // child vectors (one-hot / uniform / conditional-likelihood vector of an internal child),
@@ -775,7 +786,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
         asm volatile("bar.sync 1, %0;" ::"n"(32 * NW) : "memory");   // consumer warps only
     }
 
-    if (warp == NW) {
+    if (!DIRECT && warp == NW) {
         // ---- producer: one lane streams the items of the coefficient table; per chunk only the
         // active slot prefix m(c) * 256 bytes is copied (runs of full chunks are one copy)
         if (lane != 0) return;
@@ -935,8 +946,9 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
         for (int pass = 0; pass < npass; ++pass) {
             const uint4 mt = s_meta[(i - i_begin) * npass + pass];
             uint32_t c_lo = mt.z, c_hi = mt.w;
-            if (!(CEVB_STUB & 2)) mbar_wait_backoff(&full[s], par);
-            const double* Bq = Bs + (size_t)s * stage_doubles + lane;
+            if (!DIRECT && !(CEVB_STUB & 2)) mbar_wait_backoff(&full[s], par);
+            const double* Bq = DIRECT ? tcb + (size_t)(i * npass + pass) * F_ITEM + lane
+                                      : Bs + (size_t)s * stage_doubles + lane;
             // chunk 0 is interleaved with the epilogue of the previous item, so its DMMAs are
             // predicated per slot (SL < m(0)); the later chunks branch to the straight-line
             // variant of their slot count
@@ -951,7 +963,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
                     const double av = Aw[0];
                     double bv[M > 0 ? M : 1];
 #pragma unroll
-                    for (int sl = 0; sl < M; ++sl) bv[sl] = Bq[sl * 32];
+                    for (int sl = 0; sl < M; ++sl) bv[sl] = DIRECT ? __ldg(Bq + sl * 32) : Bq[sl * 32];
                     asm volatile("" ::: "memory");
                     auto step = [&](auto SLc) {
                         constexpr int SL = decltype(SLc)::value;
@@ -1000,14 +1012,16 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : (NW == 7 ? 2 : 4
                 const int m = (int)(c_lo & 15u);
                 const double av = Aw[(size_t)c * 32];
                 const double* Bc = Bq + (size_t)c * F_CHUNK;
-                if (!(CEVB_STUB & 4)) chunk_dispatch(m, acc, Bc, av);
+                if (!(CEVB_STUB & 4)) chunk_dispatch<DIRECT>(m, acc, Bc, av);
             }
             // every shared-memory read of this stage has been consumed by an issued DMMA (the
             // DMMAs are warp-wide, so all lanes' loads are complete)
-            if (lane == 0 && !(CEVB_STUB & 2)) mbar_arrive(&empty[s]);
-            if (++s == ns) {
-                s = 0;
-                par ^= 1u;
+            if (!DIRECT) {
+                if (lane == 0 && !(CEVB_STUB & 2)) mbar_arrive(&empty[s]);
+                if (++s == ns) {
+                    s = 0;
+                    par ^= 1u;
+                }
             }
             if (ONEPASS || pass_prev == npass - 1) finish_row(i_prev, have_prev);
             have_prev = true;
@@ -1345,7 +1359,7 @@ static int fused_query() {
 //   CEVB_TW / CEVB_TM / CEVB_TS   branch-count thresholds of the CTA shapes (launch_apply_shapes)
 //   CEVB_DENSE=1                  coefficient table without the sparse slot order (A/B runs)
 struct Tuning {
-    int tw, tm, ts, dense, skew;
+    int tw, tm, ts, td, dense, skew, ring_small, ring_medium;
 };
 static const Tuning& tuning() {
     static const Tuning t = [] {
@@ -1354,11 +1368,14 @@ static const Tuning& tuning() {
             return v ? atoi(v) : dflt;
         };
         Tuning x;
-        x.tw = env("CEVB_TW", 300);   // wide: 15 consumer warps
+        x.tw = env("CEVB_TW", 160);   // wide: 15 consumer warps
         x.tm = env("CEVB_TM", 100);   // medium: 7
         x.ts = env("CEVB_TS", 8);     // small: 3, else 1
+        x.td = env("CEVB_TD", 16);    // at most this many branches: the ring-less variant
         x.dense = env("CEVB_DENSE", 0);
         x.skew = env("CEVB_SKEW", 0);
+        x.ring_small = env("CEVB_RING_S", 1);    // ring size of the 1- and 3-warp shapes, in full items
+        x.ring_medium = env("CEVB_RING_M", 1);   // ... of the 7-warp shape
         return x;
     }();
     return t;
@@ -1384,7 +1401,8 @@ static int launch_apply_one(ApplyArgs& a, int B, cudaStream_t st) {
     const size_t one_stage = sizeof(double) * (size_t)F_ITEM;
     if (fixed + one_stage > g_f_optin) return 1;  // does not fit: caller tries a smaller variant
     size_t ring = g_f_optin - fixed;
-    size_t ring_max = (NW >= 15 ? F_MAXSTAGE : 1) * one_stage;  // narrow CTAs: more of them per SM
+    // narrow CTAs: a smaller ring, more of them per SM
+    size_t ring_max = (NW >= 15 ? F_MAXSTAGE : (NW == 7 ? tuning().ring_medium : tuning().ring_small)) * one_stage;
     if (ring > ring_max) ring = ring_max;
     a.stage_doubles_cap = (int)(ring / sizeof(double));
     a.skew = tuning().skew;
@@ -1408,6 +1426,38 @@ static int launch_apply_variant(ApplyArgs& a, int B, cudaStream_t st) {
     return launch_apply_one<G, NW, MODE, false>(a, B, st);
 }
 
+// The ring-less variant for small launches: rows are split finely over blockIdx.y so that every
+// SM holds its 16 consumer warps (16 / NW CTAs).
+template <int NW, int MODE, bool ONEPASS>
+static int launch_apply_direct(ApplyArgs& a, int B, cudaStream_t st) {
+    constexpr int EB = NW * 8;
+    const int gx = (a.n_items + EB - 1) / EB;
+    const long long want = 3LL * (16 / NW) * g_f_sm;       // three waves of resident CTAs
+    int ry = 1;
+    if ((long long)gx * B < want) {
+        ry = (int)((want + (long long)gx * B - 1) / ((long long)gx * B));
+        const int ry_max = (a.n + 7) / 8;
+        if (ry > ry_max) ry = ry_max;
+    }
+    a.rows_per_cta = (a.n + ry - 1) / ry;
+    ry = (a.n + a.rows_per_cta - 1) / a.rows_per_cta;
+    a.meta_bytes = (int)apply_meta_bytes(a.rows_per_cta * a.npass);
+    const size_t smem = apply_fixed_bytes(EB, MODE != APPLY_GENERAL ? 0 : a.ldl, a.rows_per_cta * a.npass);
+    if (smem * (16 / NW) > g_f_optin) return 1;             // large n: the ring variants take over
+    a.stage_doubles_cap = F_ITEM;
+    a.skew = 0;
+    dim3 grid(gx, ry, B);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        CEVB_CHECK_CUDA(cudaFuncSetAttribute(taylor_apply_kernel<1, NW, MODE, ONEPASS, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    taylor_apply_kernel<1, NW, MODE, ONEPASS, true><<<grid, 32 * NW, smem, st>>>(a);
+    CEVB_CHECK_LAUNCH("taylor_apply_kernel (direct)");
+    return 0;
+}
+
 template <int MODE>
 static int launch_apply_shapes(ApplyArgs& a, int B, cudaStream_t st) {
     // CTA shapes.  The kernel is latency-bound per warp (every warp alternates a DMMA phase and
@@ -1416,6 +1466,12 @@ static int launch_apply_shapes(ApplyArgs& a, int B, cudaStream_t st) {
     // (thresholds measured on B200 with tools/level_probe.py)
     int rc = 1;
     const Tuning& tn = tuning();
+    if (MODE != APPLY_EVAL && a.n_items <= tn.td) {
+        // small launches: no ring, one 8-branch group per CTA, 16 consumer warps per SM
+        rc = a.npass == 1 ? launch_apply_direct<1, MODE, true>(a, B, st)
+                          : launch_apply_direct<1, MODE, false>(a, B, st);
+        if (rc != 1) return rc;
+    }
     if (a.n_items > tn.tw) rc = launch_apply_variant<1, 15, MODE>(a, B, st);
     if (rc == 1 && a.n_items > tn.tm) rc = launch_apply_variant<1, 7, MODE>(a, B, st);
     if (rc == 1 && a.n_items > tn.ts) rc = launch_apply_variant<1, 3, MODE>(a, B, st);
