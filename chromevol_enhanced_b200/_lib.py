@@ -41,13 +41,14 @@ _PROTOTYPES = {
                                            _c.c_longlong, _c.c_void_p]),
     "cevb_taylor_doubles": (_c.c_size_t, [_c.c_int]),
     "cevb_taylor_matrices_supported": (_c.c_int, [_c.c_int]),
+    "cevb_taylor_scratch_doubles": (_c.c_size_t, [_c.c_int]),
     "cevb_taylor_prepare": (_c.c_int, [c_dp, _c.c_int, _c.c_int, _c.c_double, c_dp, c_dp, c_dp, c_dp,
                                        _c.c_void_p]),
     "cevb_expm_plan": (_c.c_int, [c_dp, c_dp, _c.c_int, _c.c_int, _c.c_longlong, c_dp, c_dp, c_dp,
                                   c_dp, c_dp, c_dp, c_dp, _c.c_void_p]),
     "cevb_taylor_matrices": (_c.c_int, [c_dp, c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, c_dp,
                                         c_dp, c_dp, _c.c_longlong, c_dp, c_dp, c_dp, c_dp, c_dp,
-                                        c_dp, _c.c_void_p]),
+                                        c_dp, c_dp, _c.c_void_p]),
     "cevb_taylor_apply": (_c.c_int, [c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, c_dp, _c.c_int,
                                      _c.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, _c.c_void_p]),
     "cevb_prune_fused": (_c.c_int, [c_dp, c_dp, c_dp, c_dp, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
@@ -105,7 +106,7 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.cevb_abi_version() != 1:
+    if lib.cevb_abi_version() != 2:
         raise CevbError("libcevb200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

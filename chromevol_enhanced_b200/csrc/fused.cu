@@ -1588,6 +1588,103 @@ __global__ void __launch_bounds__(SQ_NT, 1) square_post_kernel(double* __restric
     }
 }
 
+
+// The same for matrix orders whose two buffers do not fit in shared memory (n > 112, e.g. the
+// N = 256 shape): operands are read from global memory / L2 (a 0.5 MB matrix stays in L2), the
+// square goes to a per-CTA scratch matrix, the roles alternate.  Slower per flop than the
+// shared-memory kernel, but it keeps the series + squaring path -- and with it the fused engine
+// -- independent of the Pade kernels at every supported order.
+__global__ void __launch_bounds__(SQ_NT, 1) square_post_global_kernel(
+    double* __restrict__ X, const int32_t* __restrict__ work_s, const unsigned int* __restrict__ count,
+    long long cap, unsigned int* counter, int n, int ldp, int npad, double* __restrict__ scratch,
+    int32_t* __restrict__ nan_count) {
+    __shared__ int sh_q[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int n8 = npad >> 3;
+    long long lim = (long long)*count;
+    if (lim > cap) lim = cap;
+    double* scr = scratch + (size_t)blockIdx.x * n * ldp;
+    const int nch = (n8 + 3) >> 2, cbase = n8 / nch, cextra = n8 % nch;
+    for (;;) {
+        if (tid == 0) sh_q[0] = (int)atomicAdd(counter, 1u);
+        __syncthreads();
+        const long long q = (long long)(unsigned)sh_q[0];
+        if (q >= lim) break;
+        double* Xm = X + (size_t)q * n * ldp;
+        const int s = work_s[q];
+        double* src = Xm;
+        double* dst = scr;
+        for (int it = 0; it < s; ++it) {
+            const int ntask = n8 * nch;
+            for (int task = warp; task < ntask; task += SQ_NW) {
+                const int ch = task / n8, rt = task - ch * n8;
+                const int ct0 = ch * cbase + min(ch, cextra);
+                const int nct = cbase + (ch < cextra ? 1 : 0);
+                double acc[4][2] = {};
+                const int arow_i = rt * 8 + g;                 // row of the A fragment
+                const bool arow_ok = arow_i < n;
+                const double* arow = src + (size_t)(arow_ok ? arow_i : 0) * ldp + t4;
+                for (int k4 = 0; k4 < npad; k4 += 4) {
+                    const int kk = k4 + t4;                    // inner index of this lane
+                    const bool k_ok = kk < n;
+                    const double av = (arow_ok && k_ok) ? arow[k4] : 0.0;
+                    const double* brow = src + (size_t)(k_ok ? kk : 0) * ldp;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c < nct) {
+                            const int col = (ct0 + c) * 8 + g;
+                            const double bv = (k_ok && col < n) ? brow[col] : 0.0;
+                            dmma884(acc[c][0], acc[c][1], av, bv);
+                        }
+                    }
+                }
+                if (arow_ok) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int col = (ct0 + c) * 8 + 2 * t4;
+                        if (c < nct && col < ldp)
+                            *reinterpret_cast<double2*>(dst + (size_t)arow_i * ldp + col) =
+                                make_double2(acc[c][0], col + 1 < n ? acc[c][1] : 0.0);
+                    }
+                }
+            }
+            __syncthreads();          // global writes of this CTA are visible to all its threads
+            double* tmp = src;
+            src = dst;
+            dst = tmp;
+        }
+        // floor, renormalise, NaN check (AR:153-159); the result goes to X
+        int nanflag = 0;
+        for (int i = warp; i < n; i += SQ_NW) {
+            const double* xr = src + (size_t)i * ldp;
+            double rs = 0.0;
+            for (int j = 2 * lane; j < ldp; j += 64) {
+                const double2 x = *reinterpret_cast<const double2*>(xr + j);
+                const double a0 = (x.x != x.x) ? x.x : fmax(x.x, 1e-12);
+                const double a1 = (j + 1 < n) ? ((x.y != x.y) ? x.y : fmax(x.y, 1e-12)) : 0.0;
+                rs += a0 + a1;
+            }
+            rs = warp_sum(rs);
+            for (int j = 2 * lane; j < ldp; j += 64) {
+                const double2 x = *reinterpret_cast<const double2*>(xr + j);
+                double2 o;
+                o.x = ((x.x != x.x) ? x.x : fmax(x.x, 1e-12)) / rs;
+                o.y = (j + 1 < n) ? ((x.y != x.y) ? x.y : fmax(x.y, 1e-12)) / rs : 0.0;
+                if (o.x != o.x || o.y != o.y) nanflag = 1;
+                *reinterpret_cast<double2*>(Xm + (size_t)i * ldp + j) = o;
+            }
+        }
+        nanflag = __syncthreads_or(nanflag);
+        if (nanflag) {
+            for (int i = warp; i < n; i += SQ_NW)
+                for (int j = lane; j < ldp; j += 32) Xm[(size_t)i * ldp + j] = (i == j) ? 1.0 : 0.0;
+            if (tid == 0 && nan_count != nullptr) atomicAdd(nan_count, 1);
+        }
+        __syncthreads();
+    }
+}
+
 struct PlanRef {
     const int32_t* nc;
     const double* tau;
@@ -1673,7 +1770,13 @@ extern "C" int cevb_expm_plan(const double* norms, const double* t, int B, int E
 
 extern "C" int cevb_taylor_matrices_supported(int n) {
     if (fused_query() != 0) return 0;
-    return (n >= 2 && n <= CEVB_MAX_N && square_smem_bytes(round_up(n, 8)) <= g_f_optin) ? 1 : 0;
+    return (n >= 2 && n <= CEVB_MAX_N) ? 1 : 0;
+}
+
+extern "C" size_t cevb_taylor_scratch_doubles(int n) {
+    if (fused_query() != 0) return 0;
+    if (square_smem_bytes(round_up(n, 8)) <= g_f_optin) return 0;   // both buffers in shared memory
+    return (size_t)g_f_sm * n * ldp_of(n);                           // one matrix per persistent CTA
 }
 
 extern "C" int cevb_taylor_matrices(const double* tc, const double* norms, const int32_t* t_order,
@@ -1681,7 +1784,7 @@ extern "C" int cevb_taylor_matrices(const double* tc, const double* norms, const
                                     const int32_t* work_s, const unsigned int* count, long long cap,
                                     const int32_t* plan_nc, const double* plan_tau,
                                     const double* plan_a0, double* P, unsigned int* counter,
-                                    int32_t* nan_count, void* stream) {
+                                    int32_t* nan_count, double* scratch, void* stream) {
     if (B <= 0 || E <= 0 || cap <= 0) return 0;
     if (B > 65535) {
         set_error("cevb_taylor_matrices: B=%d exceeds one launch; chunk the batch", B);
@@ -1708,11 +1811,19 @@ extern "C" int cevb_taylor_matrices(const double* tc, const double* norms, const
     }
     if (rc != 0) return rc;
     const size_t smem = square_smem_bytes(a.npad);
-    if (smem > g_f_optin) {
-        set_error("cevb_taylor_matrices: squaring n=%d needs %zu B of shared memory", n, smem);
-        return -1;
-    }
     CEVB_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    if (smem > g_f_optin) {
+        if (scratch == nullptr) {
+            set_error("cevb_taylor_matrices: n=%d needs cevb_taylor_scratch_doubles(n) doubles of scratch", n);
+            return -1;
+        }
+        long long grid = g_f_sm;
+        if (grid > cap) grid = cap;
+        square_post_global_kernel<<<(unsigned)grid, SQ_NT, 0, st>>>(P, work_s, count, cap, counter, n,
+                                                                    a.ldp, a.npad, scratch, nan_count);
+        CEVB_CHECK_LAUNCH("square_post_global_kernel");
+        return 0;
+    }
     static size_t sq_attr = 0;
     if (smem > sq_attr) {
         CEVB_CHECK_CUDA(cudaFuncSetAttribute(square_post_kernel,

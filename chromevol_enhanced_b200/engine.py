@@ -101,6 +101,10 @@ class ExpmWorkspace:
             self.work_s = torch.zeros(max(self.p_slots, 1), dtype=torch.int32, device=device)
             self.nan_count = torch.zeros(16, dtype=torch.int32, device=device)
             self.work_count = torch.zeros(16, dtype=torch.int32, device=device)   # one per stream
+            # squarings of orders that do not fit in shared memory go through global memory:
+            # one scratch matrix per persistent CTA, per stream slice
+            sq = lib.cevb_taylor_scratch_doubles(n)
+            self.sq_scratch = torch.empty((16, sq), **f64) if sq else None
             self.w = torch.zeros((cap, n_nodes, self.ldp), **f64)
             self.wr = torch.ones((cap, n_nodes, self.ldp), **f64)
             self.mode = torch.zeros((cap, n_nodes), dtype=torch.uint8, device=device)
@@ -278,7 +282,8 @@ class LikelihoodEngine:
             _lib.check(lib.cevb_taylor_matrices(
                 P(ws.tc), P(ws.norms), _lib.ptr(self.d_t_order), nb, f.n_t, self.n, P(ws.slot),
                 Q(ws.work_s), one(ws.work_count), pps, P(ws.plan_nc), P(ws.plan_tau),
-                P(ws.plan_a0), Q(ws.P), one(ws.counter), one(ws.nan_count), st),
+                P(ws.plan_a0), Q(ws.P), one(ws.counter), one(ws.nan_count),
+                _lib.ptr(ws.sq_scratch[k]) if ws.sq_scratch is not None else _lib.ptr(None), st),
                 "cevb_taylor_matrices")
         else:
             # Pade-13 + scaling and squaring (the scipy algorithm) for the listed pairs

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define CEVB_ABI_VERSION 1
+#define CEVB_ABI_VERSION 2
 #define CEVB_NPARAM 9
 #define CEVB_NPOW 7
 #define CEVB_NNORM 16
@@ -138,11 +138,14 @@ int cevb_expm_branches_list(const double* pw, const double* norms, const uint16_
  * cevb_taylor_matrices fills the P slots of a plan: the series at t 2^-s for all listed pairs
  * of a vector at once (tensor cores, t_order = branch-length indices sorted by decreasing t),
  * then s squarings and the AR:153-159 post-processing per matrix in shared memory.
- * counter: one uint32 scratch; nan_count (may be NULL) += matrices that fell back to I. */
+ * counter: one uint32 scratch; nan_count (may be NULL) += matrices that fell back to I;
+ * scratch: cevb_taylor_scratch_doubles(n) doubles (may be NULL when that is 0). */
 size_t cevb_taylor_doubles(int n);
-/* 1 when cevb_taylor_matrices can keep two n x n matrices in shared memory (n <= 112 on B200);
- * larger orders use cevb_expm_branches_list for the pairs that need squarings */
+/* 1 for every supported order.  Up to n = 112 (B200) the squarings run with both matrices in
+ * shared memory; larger orders square through global memory / L2 and need
+ * cevb_taylor_scratch_doubles(n) doubles of scratch (0 for the shared-memory case). */
 int cevb_taylor_matrices_supported(int n);
+size_t cevb_taylor_scratch_doubles(int n);
 int cevb_taylor_prepare(const double* pw, int B, int n, double t_max, double* norms, uint16_t* csc,
                         uint8_t* csc_cnt, double* tc, void* stream);
 int cevb_expm_plan(const double* norms, const double* t, int B, int E, long long cap, int32_t* slot,
@@ -152,7 +155,7 @@ int cevb_taylor_matrices(const double* tc, const double* norms, const int32_t* t
                          int n, const int32_t* slot, const int32_t* work_s,
                          const unsigned int* count, long long cap, const int32_t* plan_nc,
                          const double* plan_tau, const double* plan_a0, double* P,
-                         unsigned int* counter, int32_t* nan_count, void* stream);
+                         unsigned int* counter, int32_t* nan_count, double* scratch, void* stream);
 
 /* ---- (2d+3) fused transition-probability x child-vector product, AR:136-166 + AR:237 without
  * materialising P: for every listed branch (items[k] = child node id, branch length

@@ -227,16 +227,19 @@ def _series_matrices(rows, times, N):
                                         _lib.ptr(ws.slot), _lib.ptr(ws.work_s), _lib.ptr(ws.work_count),
                                         B * E, _lib.ptr(ws.plan_nc), _lib.ptr(ws.plan_tau),
                                         _lib.ptr(ws.plan_a0), _lib.ptr(ws.P), _lib.ptr(ws.counter),
-                                        _lib.ptr(ws.nan_count), st), "matrices")
+                                        _lib.ptr(ws.nan_count),
+                                        _lib.ptr(ws.sq_scratch[0]) if ws.sq_scratch is not None else _lib.ptr(None),
+                                        st), "matrices")
     torch.cuda.synchronize()
     cnt = int(ws.work_count[0])
     return (ws.P[:cnt, :, :n].cpu().numpy(), ws.slot.cpu().numpy(), ws.work_s[:cnt].cpu().numpy(),
             int(ws.nan_count[0]))
 
 
-@pytest.mark.parametrize("N", [35, 100, 111])
+@pytest.mark.parametrize("N", [35, 100, 111, 140, 256])
 def test_series_squaring_matrices_match_oracle(N):
-    """Pairs beyond the switch-over: series at t 2^-s, s squarings, post-processing."""
+    """Pairs beyond the switch-over: series at t 2^-s, s squarings, post-processing.  N <= 111
+    squares in shared memory, the larger orders through global memory."""
     from chromevol_enhanced_b200 import synthetic
     rows = synthetic.random_param_rows(8, seed=4, linear='positive')
     rows[:, :5] *= 4.0
@@ -261,22 +264,26 @@ def test_series_squaring_matrices_match_oracle(N):
     assert n_checked >= 20
 
 
-def test_large_order_falls_back_to_pade_squaring():
-    """n = 257: two matrices do not fit in shared memory, so the fused engine routes the pairs
-    that need squarings to the Pade kernel."""
+@pytest.mark.parametrize("squaring", ["series", "pade"])
+def test_large_order_squaring_paths(squaring):
+    """n = 257: two matrices do not fit in shared memory; the series path squares through global
+    memory (the default), the Pade kernels remain selectable.  Both against the oracle."""
     from chromevol_enhanced_b200 import _lib, synthetic
     from chromevol_enhanced_b200.engine import LikelihoodEngine
     from chromevol_enhanced_b200.flatten import FlatTree
     assert _lib.load().cevb_taylor_matrices_supported(101) == 1
-    assert _lib.load().cevb_taylor_matrices_supported(257) == 0
+    assert _lib.load().cevb_taylor_matrices_supported(257) == 1
+    assert _lib.load().cevb_taylor_scratch_doubles(101) == 0
+    assert _lib.load().cevb_taylor_scratch_doubles(257) > 0
     tree = synthetic.random_tree(30, seed=41, mean_len=0.15)
     counts = synthetic.simulate_tip_counts(tree, 256, seed=42, root_state=40)
     rows = synthetic.random_param_rows(3, seed=43, linear='positive')
     rows[:, 7] *= 0.1
     flat = FlatTree(tree, counts, 256)
-    eng = LikelihoodEngine(flat, path="fused")
-    assert eng.squaring == "pade"
+    eng = LikelihoodEngine(flat, path="fused", squaring=squaring)
+    assert eng.squaring == squaring
     a = eng.log_likelihood(rows).cpu().numpy()
+    assert int(eng._materialised) > 0, "the case is meant to exercise the squaring path"
     for b in range(rows.shape[0]):
         ref, _, _ = O.log_likelihood(tree, counts, 256, synthetic.row_to_dict(rows[b]))
         assert a[b] == pytest.approx(ref, rel=1e-9), b

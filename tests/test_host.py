@@ -90,7 +90,7 @@ def test_abi_library_loads_and_exports_header_symbols():
     for name in declared:
         assert hasattr(lib, name), name
     typed = _lib.load()
-    assert typed.cevb_abi_version() == 1
+    assert typed.cevb_abi_version() == 2
     assert typed.cevb_ldq(101) == 102 and typed.cevb_ldp(36) == 36
 
 
