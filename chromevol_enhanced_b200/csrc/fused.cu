@@ -60,8 +60,23 @@ __host__ __device__ inline int taylor_npass(int n) { return ((n + 7) / 8 + F_JT 
 __host__ __device__ inline size_t taylor_data_doubles(int n) {
     return (size_t)n * taylor_npass(n) * F_ITEM;
 }
-__host__ __device__ inline size_t taylor_vec_doubles(int n) {
+// Low-precision copy of the coefficients for the leaf launch (n <= 104, generator Q only): the
+// floor correction sum_j max(1e-12 - P_ij, 0) of a leaf branch is at most 1e-10 and is needed to
+// about 1 % (see leaf_lowp_kernel), so it is formed on the TF32 tensor cores from
+//     P_ij = sum_k That[e][k] Chat_k[i][j],  That = e^{-mu t} (nu t)^k / k!,  Chat_k = ((Q + mu I) / nu)^k,
+// both factors in [0, 1].  tf[row][k-block of 8 degrees][tile 13][lane 32][2]: the B fragment of
+// mma.m16n8k8.tf32 (lane 4g+t holds degrees t and t+4 of column g of the tile).
+constexpr int L_KB = F_KC / 2;                  // k-blocks of 8 degrees
+constexpr int L_TILE = 64;                      // floats per (k-block, tile)
+constexpr int L_ROW = L_KB * F_JT * L_TILE;     // floats per row
+__host__ __device__ inline size_t taylor_lowp_doubles(int n) {
+    return taylor_npass(n) == 1 ? (size_t)n * L_ROW / 2 : 0;
+}
+__host__ __device__ inline size_t taylor_meta_end_doubles(int n) {
     return taylor_data_doubles(n) + (size_t)n * taylor_npass(n) * F_META;
+}
+__host__ __device__ inline size_t taylor_vec_doubles(int n) {
+    return taylor_meta_end_doubles(n) + taylor_lowp_doubles(n);
 }
 
 // The series is summed for the SHIFTED matrix (uniformisation): with mu = max(0, -min_i Q_ii),
@@ -152,11 +167,13 @@ __global__ void __launch_bounds__(128) q_structure_kernel(const double* __restri
     const double mu = block_max(dmax);
     // column pass: structure, ||Q||_1, ||Q + mu I||_1
     double best = 0.0, best_s = 0.0;
+    bool negoff = false;   // a negative (or non-finite) off-diagonal entry: Q is no generator
     for (int j = tid; j < n; j += 128) {
         int cc = 0;
         double sum = 0.0, sum_s = 0.0;
         for (int i = 0; i < n; ++i) {
             const double q = Q[(size_t)i * ldq + j];
+            if (i != j && !(q >= 0.0 && q < INFINITY)) negoff = true;
             if (q != 0.0) {  // NaN != 0 is true: kept as "non-zero"
                 if (cc < CEVB_MAX_SPARSE) idx_c[(size_t)cc * n + j] = (uint16_t)i;
                 ++cc;
@@ -183,11 +200,14 @@ __global__ void __launch_bounds__(128) q_structure_kernel(const double* __restri
     const double nu1 = block_max(best_s);
     const double nui = block_max(best_r);
     const bool anynan = __syncthreads_or(nan);
+    const bool anyneg = __syncthreads_or(negoff);
     if (tid == 0) {
         double* out = norms + (size_t)b * CEVB_NNORM;
+        const double nu = fmin(nu1, nui);
         out[CEVB_NORM_ONE] = anynan ? NAN : one;   // numpy max propagates NaN
         out[CEVB_NORM_SHIFT] = anynan ? NAN : mu;
-        out[CEVB_NORM_SHIFTED] = anynan ? NAN : fmin(nu1, nui);
+        out[CEVB_NORM_SHIFTED] = anynan ? NAN : nu;
+        out[CEVB_NORM_GENERATOR] = (!anynan && !anyneg && nu > 0.0 && nu < INFINITY) ? 1.0 : 0.0;
     }
 }
 
@@ -205,7 +225,8 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
                                                            const uint8_t* __restrict__ csc_cnt,
                                                            const double* __restrict__ norms,
                                                            int n, int ldq, int npad, double t_max,
-                                                           int dense, double* __restrict__ tc) {
+                                                           int dense, int lowp_on,
+                                                           double* __restrict__ tc) {
     extern __shared__ double shc[];
     double* cur = shc;                    // [TCR][npad]
     double* nxt = shc + TCR * npad;       // [TCR][npad]
@@ -223,6 +244,12 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
     const uint8_t* cnt_c = csc_cnt + (size_t)b * 2 * n;
     double* tcb = tc + (size_t)b * taylor_vec_doubles(n);
     const double mu = norms[(size_t)b * CEVB_NNORM + CEVB_NORM_SHIFT];
+    // low-precision copy (see taylor_lowp_doubles): generator vectors with one pass per row
+    const double nu_l = norms[(size_t)b * CEVB_NNORM + CEVB_NORM_SHIFTED];
+    const bool lowp = lowp_on && npass == 1 && norms[(size_t)b * CEVB_NNORM + CEVB_NORM_GENERATOR] != 0.0;
+    float* tfb = reinterpret_cast<float*>(tcb + taylor_meta_end_doubles(n));
+    double scl = 1.0;          // k! / nu^k of the current degree
+    double sc4[4] = {1.0, 1.0, 1.0, 1.0};
     // chunks any branch of this vector can need: the longest branch decides (all of them when
     // it has to be scaled and squared, or when the caller gives no bound)
     int kc_need = F_KC;
@@ -274,6 +301,8 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
     const int cmax = __reduce_max_sync(0xffffffffu, (j0 < n && cnt0 != 255) ? cnt0 : 0);
     __syncthreads();
     for (int k = 0; k < k_end; ++k) {
+        sc4[k & 3] = scl;
+        scl *= (double)(k + 1) / nu_l;
         for (int j = tid; j < npad; j += 128) {
 #pragma unroll
             for (int r = 0; r < TCR; ++r)
@@ -323,6 +352,25 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
         __syncthreads();
         if ((k & 3) == 3) {
             const int c = k >> 2;
+            if (lowp && tid < F_JT * 8) {
+                // scaled TF32 copy of this chunk in mma.m16n8k8 B-fragment order (and zeros for
+                // the other half of the k-block if the table ends with this chunk)
+                const int tile = tid >> 3, g8 = tid & 7, kb = c >> 1, half = c & 1;
+                const bool tail = (c == kc_need - 1) && half == 0;
+                for (int r = 0; r < TCR; ++r) {
+                    if (i0 + r >= n) break;
+                    float* dst = tfb + (((size_t)(i0 + r) * L_KB + kb) * F_JT + tile) * L_TILE;
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        // all 13 tiles are written: columns beyond npad are zeros
+                        const float v = tid < npad ? (float)(stg[((size_t)r * npad + tid) * 4 + d] * sc4[d]) : 0.0f;
+                        uint32_t u;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+                        dst[(g8 * 4 + d) * 2 + half] = __uint_as_float(u);
+                        if (tail) dst[(g8 * 4 + d) * 2 + 1] = 0.0f;
+                    }
+                }
+            }
             // which tiles of this chunk hold a non-zero (a tile is 32 contiguous doubles of stg;
             // NaN counts as non-zero)
             for (int x = warp; x < TCR * nj; x += 4) {
@@ -508,6 +556,7 @@ struct ApplyArgs {
     int meta_bytes;           // shared memory for the per-item meta data of a CTA's rows
     int stage_doubles_cap;    // doubles available for the coefficient ring
     int skew;                 // experiment: clocks by which every other warp of a scheduler starts late
+    int skip_generators;      // leaf launch: generator vectors are handled by leaf_lowp_kernel
     // EVAL mode: items index the branch-length array t_node [E]; the raw series value at
     // t 2^-s goes to X[slot[b * E + item]] (n rows of ldp doubles) for the squaring kernel
     const int32_t* slot;
@@ -656,6 +705,9 @@ __global__ void __launch_bounds__(32 * (NW + (DIRECT ? 0 : 1)),
     double* Ls = As + (size_t)(EB / 8) * F_KC * 32;                           // [EB][ldl] (not LEAF)
     double* Bs = Ls + (LEAF ? 0 : (size_t)EB * ldl);                          // ring of item tiles
 
+    if (MODE == APPLY_LEAF && a.skip_generators &&
+        a.norms[(size_t)b * CEVB_NNORM + CEVB_NORM_GENERATOR] != 0.0)
+        return;
     if (EVAL) {
         // The launch covers every (vector, branch length) pair, but only the few pairs whose
         // series needs squarings have work here.  The list is ordered by decreasing length and
@@ -1060,6 +1112,302 @@ __global__ void __launch_bounds__(32 * (NW + (DIRECT ? 0 : 1)),
 }
 
 // ---------------------------------------------------------------------------------------------
+// Leaf launch for generator vectors (n <= 104): w = max(P[i][code], 1e-12) and
+// wr = sum_j max(P[i][j], 1e-12) for every observed-leaf branch, without the FP64 matrix.
+//
+// For a generator Q the rows of P = expm(Q t) sum to one, so
+//     wr_i = 1 + corr_i,   corr_i = sum_j max(1e-12 - P_ij, 0)  <=  n * 1e-12.
+// The reference's result P'_ic = max(P_ic, 1e-12) / wr_i therefore needs P_ic in full precision
+// (one column: a dot product of length `terms` per row, summed here from the FP64 table), but
+// corr_i only to about 1 % for an absolute error of 1e-12 in P' -- the tolerance of the parity
+// tests; the log-likelihood tolerance is another three orders looser.  corr_i comes from the full
+// matrix in TF32 on the tensor cores (mma.sync.m16n8k8, FP32 accumulation of non-negative terms
+// scaled into [0, 1]: relative error about 1e-3 on the entries near the floor, 1e-13 absolute on
+// wr), at an eighth of the issue slots of the FP64 DMMA path and without its epilogue.
+// Vectors whose Q is no generator (negative linear_rate) keep the FP64 kernel: there the rows do
+// not sum to one and negative entries of any size are floored.
+struct LowpArgs {
+    const double* tc;
+    const double* norms;
+    const int32_t* items;
+    const int32_t* leaf_code;
+    double* w;
+    double* wr;
+    uint8_t* mode;
+    int n_items, n, ldp, n_nodes, E;
+    const int32_t* plan_nc;
+    const double* plan_tau;
+    const double* plan_a0;
+    const int32_t* branch_of;
+    int ring_floats;          // floats available for the ring of TF32 row tiles
+};
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const float4& a, const float2& b) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)),
+          "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)));
+}
+
+constexpr int LP_MAXSTAGE = 4;
+
+__host__ __device__ inline size_t lowp_fixed_bytes(int nw, int n) {
+    const int eb = nw * 16;
+    size_t b = 16 * LP_MAXSTAGE + 4 * (3 * eb + 4);            // barriers, child / code / terms
+    b = (b + 127) / 128 * 128;
+    b += (size_t)((16 * n + 127) / 128) * 128;                 // per-row meta (inv, counts)
+    b += sizeof(double) * (size_t)(eb / 8) * F_KC * 32;        // FP64 t^k table (column dot product)
+    b += sizeof(float) * (size_t)nw * L_KB * 32 * 4;           // TF32 A fragments
+    return b;
+}
+
+// One CTA: vector blockIdx.z, branches [blockIdx.x * 16 NW, +16 NW) of the leaf list, rows
+// [blockIdx.y * rows_per_cta, ...).  NW consumer warps of 16 branches each + one producer warp
+// that streams the TF32 row tiles through a ring of shared-memory stages.
+template <int NW>
+__global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : 2)
+    leaf_lowp_kernel(LowpArgs a, int rows_per_cta) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    constexpr int EB = NW * 16;
+    const int b = blockIdx.z, n = a.n;
+    if (a.norms[(size_t)b * CEVB_NNORM + CEVB_NORM_GENERATOR] == 0.0) return;   // FP64 kernel's vector
+    const int e0 = blockIdx.x * EB;
+    const int i_begin = blockIdx.y * rows_per_cta;
+    const int i_end = min(n, i_begin + rows_per_cta);
+
+    uint64_t* full = reinterpret_cast<uint64_t*>(smraw);
+    uint64_t* empty = full + LP_MAXSTAGE;
+    int* s_child = reinterpret_cast<int*>(smraw + 16 * LP_MAXSTAGE);
+    int* s_code = s_child + EB;
+    int* s_nc = s_code + EB;
+    size_t off = (16 * LP_MAXSTAGE + 4 * (3 * EB + 4) + 127) / 128 * 128;
+    uint4* s_meta = reinterpret_cast<uint4*>(smraw + off);
+    off += (size_t)((16 * n + 127) / 128) * 128;
+    double* As = reinterpret_cast<double*>(smraw + off);                       // [EB/8][F_KC][32]
+    off += sizeof(double) * (size_t)(EB / 8) * F_KC * 32;
+    float* Tf = reinterpret_cast<float*>(smraw + off);                          // [NW][L_KB][32][4]
+    off += sizeof(float) * (size_t)NW * L_KB * 32 * 4;
+    float* Bs = reinterpret_cast<float*>(smraw + off);                          // ring
+
+    const double* tcb = a.tc + (size_t)b * taylor_vec_doubles(n);
+    const float* tfb = reinterpret_cast<const float*>(tcb + taylor_meta_end_doubles(n));
+    const double nu = a.norms[(size_t)b * CEVB_NNORM + CEVB_NORM_SHIFTED];
+    {
+        const unsigned long long* mg =
+            reinterpret_cast<const unsigned long long*>(tcb + taylor_data_doubles(n)) + (size_t)i_begin * F_META;
+        for (int x = tid; x < i_end - i_begin; x += blockDim.x) {
+            const unsigned long long w0 = mg[(size_t)x * F_META + 2];   // inv: tile -> slot
+            const unsigned long long w1 = mg[(size_t)x * F_META + 1];   // counts
+            s_meta[x] = make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
+        }
+    }
+    for (int x = tid; x < NW * L_KB * 32 * 4; x += blockDim.x) Tf[x] = 0.0f;
+    __syncthreads();
+    for (int x = tid; x < EB; x += blockDim.x) {
+        const int e = e0 + x;
+        int nc = 0, child = -1, code = -2;
+        double tau = 0.0, a0 = 0.0;
+        if (e < a.n_items) {
+            child = a.items[e];
+            code = a.leaf_code[child];
+            const size_t pi = (size_t)b * a.E + (a.branch_of ? a.branch_of[child] : child);
+            const int pn = a.plan_nc[pi];
+            if ((pn >> 8) != 0) {
+                a.mode[(size_t)b * a.n_nodes + child] = (uint8_t)(pn >> 8);   // identity / materialised
+            } else {
+                nc = pn & 0xff;
+                tau = a.plan_tau[pi];
+                a0 = a.plan_a0[pi];
+            }
+        }
+        s_child[x] = child;
+        s_code[x] = code;
+        s_nc[x] = nc;
+        double* arow = As + (size_t)(x >> 3) * F_KC * 32 + (x & 7) * 4;
+        // A fragment of mma.m16n8k8 (row-major 16 x 8): lane 4g+t holds (row g, k t), (row g+8, k t),
+        // (row g, k t+4), (row g+8, k t+4)
+        float* trow = Tf + (size_t)(x >> 4) * L_KB * 128;
+        const int r16 = x & 15, gg = r16 & 7, hi = r16 >> 3;
+        double p = a0;        // e^{-mu tau} tau^k
+        double fk = 1.0;      // nu^k / k!
+        for (int k = 0; k < 4 * F_KC; ++k) {
+            arow[(k >> 2) * 32 + (k & 3)] = (k < nc) ? p : 0.0;
+            if (k < nc) {
+                const float v = (float)(p * fk);
+                uint32_t u;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+                const int kk = k & 7;
+                trow[((k >> 3) * 32 + gg * 4 + (kk & 3)) * 4 + hi + 2 * (kk >> 2)] = __uint_as_float(u);
+            }
+            p *= tau;
+            fk *= nu / (double)(k + 1);
+        }
+    }
+    __syncthreads();
+
+    int wk = 0, ck = 0;      // 8-degree blocks needed by this warp / by the CTA
+    unsigned active = 0;
+    for (int x = lane; x < EB; x += 32) {
+        const int kb = (s_nc[x] + 7) >> 3;
+        ck = max(ck, kb);
+        if (kb > 0) active |= 1u << (x >> 4);
+        if ((x >> 4) == warp) wk = max(wk, kb);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wk = max(wk, __shfl_xor_sync(0xffffffffu, wk, o));
+        ck = max(ck, __shfl_xor_sync(0xffffffffu, ck, o));
+        active |= __shfl_xor_sync(0xffffffffu, active, o);
+    }
+    if (ck == 0) return;
+    const int stage_floats = ck * F_JT * L_TILE;
+    int ns = a.ring_floats / stage_floats;
+    if (ns > LP_MAXSTAGE) ns = LP_MAXSTAGE;
+    if (tid == 0) {
+        for (int s = 0; s < ns; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], __popc(active));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        if (lane != 0) return;
+        int s = 0, use = 0;
+        const uint32_t bytes = (uint32_t)stage_floats * sizeof(float);
+        for (int i = i_begin; i < i_end; ++i) {
+            if (use > 0) mbar_wait_backoff(&empty[s], (uint32_t)((use - 1) & 1));
+            mbar_expect_tx(&full[s], bytes);
+            bulk_g2s(Bs + (size_t)s * stage_floats, tfb + (size_t)i * L_ROW, bytes, &full[s]);
+            if (++s == ns) {
+                s = 0;
+                ++use;
+            }
+        }
+        return;
+    }
+    if (wk == 0) return;
+
+    // ---- consumers: 16 branches per warp
+    const int xq = warp * 16 + (lane >> 1);            // the branch whose column this lane pair sums
+    const int part = lane & 1;
+    const int q_code = s_code[xq], q_child = s_child[xq];
+    const int q_kc = (s_nc[xq] + 3) >> 2;              // its 4-degree chunks
+    const bool q_ok = q_child >= 0 && q_kc > 0 && q_code >= 0;
+    const int q_tile = q_ok ? (q_code >> 3) : 0, q_col = q_code & 7;
+    const double* q_T = As + (size_t)(xq >> 3) * F_KC * 32 + (xq & 7) * 4;
+    const size_t vb = (size_t)b * a.n_nodes * a.ldp;
+    // columns >= n of the last tile hold zeros: they count 1e-12 each and are taken out again
+    float padfix;
+    {
+        int cnt = 0;
+        for (int j = 2 * t4; j < F_JT * 8; j += 8) cnt += (j >= n) + (j + 1 >= n);
+        padfix = (float)cnt * 1e-12f;
+    }
+    const float4* Tw = reinterpret_cast<const float4*>(Tf) + (size_t)warp * L_KB * 32 + lane;
+    int s = 0;
+    uint32_t par = 0;
+    for (int i = i_begin; i < i_end; ++i) {
+        const uint4 mt = s_meta[i - i_begin];
+        // (1) this lane pair's column of P in FP64 from the coefficient table (chunks of the
+        // branch alternate between the two lanes); the loads are in flight during the MMAs
+        double col = 0.0;
+        constexpr int PF = 3;                 // chunks per lane whose loads fly during the MMAs
+        double2 cf[PF][2];
+        bool has[PF];
+        int slot = 0;
+        unsigned long long cnts = 0ull;
+        const double* base = tcb;
+        if (q_ok) {
+            const uint32_t invw = (q_tile < 8) ? mt.x : mt.y;
+            slot = (int)((invw >> (4 * (q_tile & 7))) & 15u);
+            cnts = ((unsigned long long)mt.w << 32) | mt.z;
+            base = tcb + (size_t)i * F_ITEM + slot * 32 + q_col * 4;
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int c = part + 2 * u;
+            has[u] = q_ok && c < q_kc && slot < (int)((cnts >> (4 * c)) & 15ull);
+            if (has[u]) {
+                cf[u][0] = __ldg(reinterpret_cast<const double2*>(base + (size_t)c * F_CHUNK));
+                cf[u][1] = __ldg(reinterpret_cast<const double2*>(base + (size_t)c * F_CHUNK) + 1);
+            }
+        }
+        // (2) the whole row in TF32
+        mbar_wait_backoff(&full[s], par);
+        const float2* Bq = reinterpret_cast<const float2*>(Bs + (size_t)s * stage_floats) + lane;
+        float acc[F_JT][4];
+#pragma unroll
+        for (int jt = 0; jt < F_JT; ++jt) acc[jt][0] = acc[jt][1] = acc[jt][2] = acc[jt][3] = 0.0f;
+        for (int kb = 0; kb < wk; ++kb) {
+            const float4 af = Tw[(size_t)kb * 32];
+            const float2* Bk = Bq + (size_t)kb * F_JT * 32;
+#pragma unroll
+            for (int jt = 0; jt < F_JT; ++jt) mma_tf32_16x8x8(acc[jt], af, Bk[jt * 32]);
+        }
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == ns) {
+            s = 0;
+            par ^= 1u;
+        }
+        // (1b) the column dot product from the loads issued above (and the rare later chunks)
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            if (has[u]) {
+                const int c = part + 2 * u;
+                const double2 t01 = *reinterpret_cast<const double2*>(q_T + c * 32);
+                const double2 t23 = *reinterpret_cast<const double2*>(q_T + c * 32 + 2);
+                col = fma(t01.x, cf[u][0].x, col);
+                col = fma(t01.y, cf[u][0].y, col);
+                col = fma(t23.x, cf[u][1].x, col);
+                col = fma(t23.y, cf[u][1].y, col);
+            }
+        }
+        if (q_ok) {
+            for (int c = part + 2 * PF; c < q_kc; c += 2) {
+                if (slot < (int)((cnts >> (4 * c)) & 15ull)) {
+                    const double2 c01 = __ldg(reinterpret_cast<const double2*>(base + (size_t)c * F_CHUNK));
+                    const double2 c23 = __ldg(reinterpret_cast<const double2*>(base + (size_t)c * F_CHUNK) + 1);
+                    const double2 t01 = *reinterpret_cast<const double2*>(q_T + c * 32);
+                    const double2 t23 = *reinterpret_cast<const double2*>(q_T + c * 32 + 2);
+                    col = fma(t01.x, c01.x, col);
+                    col = fma(t01.y, c01.y, col);
+                    col = fma(t23.x, c23.x, col);
+                    col = fma(t23.y, c23.y, col);
+                }
+            }
+        }
+        // (3) corr = sum_j max(1e-12 - P_ij, 0) for rows g and g + 8 of the group
+        float c0 = -padfix, c1 = -padfix;
+#pragma unroll
+        for (int jt = 0; jt < F_JT; ++jt) {
+            c0 += fmaxf(1e-12f - acc[jt][0], 0.0f) + fmaxf(1e-12f - acc[jt][1], 0.0f);
+            c1 += fmaxf(1e-12f - acc[jt][2], 0.0f) + fmaxf(1e-12f - acc[jt][3], 0.0f);
+        }
+        c0 += __shfl_xor_sync(0xffffffffu, c0, 1);
+        c0 += __shfl_xor_sync(0xffffffffu, c0, 2);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, 1);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
+        // branch (lane >> 1) of the group: rows 0..7 sit in c0 of quad g, rows 8..15 in c1
+        const int r16 = lane >> 1;
+        const float cq0 = __shfl_sync(0xffffffffu, c0, (r16 & 7) * 4);
+        const float cq1 = __shfl_sync(0xffffffffu, c1, (r16 & 7) * 4);
+        col += __shfl_xor_sync(0xffffffffu, col, 1);
+        if (part == 0 && q_ok) {
+            const double corr = (double)((r16 < 8) ? cq0 : cq1);
+            const unsigned int o = (unsigned)q_child * (unsigned)a.ldp + (unsigned)i;
+            (a.w + vb)[o] = (col < 1e-12) ? 1e-12 : col;          // AR:153 on the one entry that is read
+            (a.wr + vb)[o] = 1.0 + corr;                           // AR:154: rows of a generator sum to one
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 constexpr int CT = 128;
 
 __device__ double block_sum_ct(double v, double* red) {
@@ -1359,7 +1707,7 @@ static int fused_query() {
 //   CEVB_TW / CEVB_TM / CEVB_TS   branch-count thresholds of the CTA shapes (launch_apply_shapes)
 //   CEVB_DENSE=1                  coefficient table without the sparse slot order (A/B runs)
 struct Tuning {
-    int tw, tm, ts, td, dense, skew, ring_small, ring_medium;
+    int tw, tm, ts, td, dense, skew, ring_small, ring_medium, lowp;
 };
 static const Tuning& tuning() {
     static const Tuning t = [] {
@@ -1376,6 +1724,7 @@ static const Tuning& tuning() {
         x.skew = env("CEVB_SKEW", 0);
         x.ring_small = env("CEVB_RING_S", 1);    // ring size of the 1- and 3-warp shapes, in full items
         x.ring_medium = env("CEVB_RING_M", 1);   // ... of the 7-warp shape
+        x.lowp = env("CEVB_LOWP", 1);            // TF32 floor correction for the leaf launch
         return x;
     }();
     return t;
@@ -1685,6 +2034,44 @@ __global__ void __launch_bounds__(SQ_NT, 1) square_post_global_kernel(
     }
 }
 
+template <int NW>
+static int launch_leaf_lowp(const ApplyArgs& src, int B, cudaStream_t st) {
+    LowpArgs a;
+    a.tc = src.tc; a.norms = src.norms; a.items = src.items; a.leaf_code = src.leaf_code;
+    a.w = src.w; a.wr = src.wr; a.mode = src.mode;
+    a.n_items = src.n_items; a.n = src.n; a.ldp = src.ldp; a.n_nodes = src.n_nodes; a.E = src.E;
+    a.plan_nc = src.plan_nc; a.plan_tau = src.plan_tau; a.plan_a0 = src.plan_a0; a.branch_of = src.branch_of;
+    constexpr int EB = NW * 16;
+    const int gx = (a.n_items + EB - 1) / EB;
+    const long long want = 4LL * g_f_sm;
+    int ry = 1;
+    if ((long long)gx * B < want) {
+        ry = (int)((want + (long long)gx * B - 1) / ((long long)gx * B));
+        const int ry_max = (a.n + 7) / 8;
+        if (ry > ry_max) ry = ry_max;
+    }
+    const int rows_per_cta = (a.n + ry - 1) / ry;
+    ry = (a.n + rows_per_cta - 1) / rows_per_cta;
+    const size_t fixed = lowp_fixed_bytes(NW, a.n);
+    const size_t one_stage = sizeof(float) * (size_t)L_ROW;
+    const size_t budget = g_f_optin / 2 - 2048;               // two CTAs per SM (1 KB reserved each)
+    if (fixed + one_stage > budget) return 1;
+    size_t ring = budget - fixed;
+    if (ring > LP_MAXSTAGE * one_stage) ring = LP_MAXSTAGE * one_stage;
+    a.ring_floats = (int)(ring / sizeof(float));
+    const size_t smem = fixed + ring;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        CEVB_CHECK_CUDA(cudaFuncSetAttribute(leaf_lowp_kernel<NW>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    dim3 grid(gx, ry, B);
+    leaf_lowp_kernel<NW><<<grid, 32 * (NW + 1), smem, st>>>(a, rows_per_cta);
+    CEVB_CHECK_LAUNCH("leaf_lowp_kernel");
+    return 0;
+}
+
 struct PlanRef {
     const int32_t* nc;
     const double* tau;
@@ -1714,6 +2101,14 @@ static int launch_apply(const double* tc, const double* norms, int B, int n, int
     if ((a.ldl % 16) == 0) a.ldl += 8;
     a.slot = nullptr; a.X = nullptr; a.E = plan.E;
     a.plan_nc = plan.nc; a.plan_tau = plan.tau; a.plan_a0 = plan.a0; a.branch_of = plan.branch_of;
+    a.skip_generators = 0;
+    if (leaf_only && tuning().lowp && a.npass == 1) {
+        // generator vectors: column in FP64 + floor correction on the TF32 tensor cores; the
+        // FP64 launch below then only works on the vectors whose Q is no generator
+        const int rl = launch_leaf_lowp<7>(a, B, st);
+        if (rl < 0) return rl;
+        if (rl == 0) a.skip_generators = 1;
+    }
     const int rc = leaf_only ? launch_apply_shapes<APPLY_LEAF>(a, B, st)
                              : launch_apply_shapes<APPLY_GENERAL>(a, B, st);
     if (rc == 1) {
@@ -1749,7 +2144,7 @@ extern "C" int cevb_taylor_prepare(const double* pw, int B, int n, double t_max,
         coeff_attr = csm;
     }
     taylor_coeff_kernel<<<grid, 128, csm, st>>>(
-        pw, csc, csc_cnt, norms, n, ldq_of(n), npad, t_max, tuning().dense, tc);
+        pw, csc, csc_cnt, norms, n, ldq_of(n), npad, t_max, tuning().dense, tuning().lowp, tc);
     CEVB_CHECK_LAUNCH("taylor_coeff_kernel");
     return 0;
 }
@@ -1803,6 +2198,7 @@ extern "C" int cevb_taylor_matrices(const double* tc, const double* norms, const
     a.ldl = 0;
     a.npass = taylor_npass(n);
     a.slot = slot; a.X = P; a.E = E;
+    a.skip_generators = 0;
     a.plan_nc = plan_nc; a.plan_tau = plan_tau; a.plan_a0 = plan_a0; a.branch_of = nullptr;
     int rc = launch_apply_shapes<APPLY_EVAL>(a, B, st);
     if (rc == 1) {
