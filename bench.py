@@ -378,11 +378,18 @@ def run_ours(args):
     s_list = np.concatenate([x[0].reshape(-1) for x in info_log])    # squarings of the listed pairs
     norms = np.concatenate([x[2] for x in info_log])
     nu, mu = norms[:, 12], norms[:, 11]                   # CEVB_NORM_SHIFTED, CEVB_NORM_SHIFT
-    work = accounting.fused_work(flat, nu, mu)
+    # generator vectors (all of this workload): their observed-leaf branches run in
+    # leaf_lowp_kernel (FP64 column + TF32 floor correction), everything else in the FP64 kernel
+    lowp = accounting.is_generator_row(rows, n) & (os.environ.get("CEVB_LOWP", "1") != "0")
+    work = accounting.fused_work(flat, nu, mu, lowp_leaf=lowp)
     t_stage = {k: v * 1e-3 / steps for k, v in stage_ms.items()}
-    apply_s, combine_s = t_stage.get("apply", 0.0), t_stage.get("combine", 0.0)
+    leaf_s = t_stage.get("leaf", 0.0)
+    # the FP64 tensor kernel: every level launch, plus the leaf launch when no vector takes the
+    # TF32 path
+    apply_s = t_stage.get("apply", 0.0) + (0.0 if lowp.any() else leaf_s)
+    combine_s = t_stage.get("combine", 0.0)
     expm_s, prep_s, init_s = t_stage.get("expm", 0.0), t_stage.get("prepare", 0.0), t_stage.get("init", 0.0)
-    apply_launches = max(n_chunks * (int(flat.leaf_child.size > 0) +
+    apply_launches = max(n_chunks * (int(flat.leaf_child.size > 0 and not lowp.all()) +
                                      int(np.count_nonzero(np.diff(flat.level_child_off)))), 1)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -412,7 +419,7 @@ def run_ours(args):
     # what the reference's algorithm (one Pade-13 expm per branch) would have cost,
     # counted without any squarings (a lower bound)
     pade_equiv = float(accounting.pade_flops(n, 0)) * B * flat.n_branches
-    pade_equiv_tf = pade_equiv / (apply_s + expm_s + prep_s) / 1e12 if apply_s > 0 else None
+    pade_equiv_tf = pade_equiv / (apply_s + leaf_s + expm_s + prep_s) / 1e12 if apply_s > 0 else None
     # combine kernel: reads w (or streams a materialised P) and writes the node vectors
     combine_bytes = 8.0 * (work["fused_pairs"] * n + B * flat.n_nodes * n) + \
         8.0 * float(list_pairs) * (n * n + n)
@@ -451,8 +458,25 @@ def run_ours(args):
                      "executed_frac": (apply_exec_tf / fp64_peak) if apply_exec_tf else None,
                      "share_of_step": apply_s / max(sum(t_stage.values()), 1e-12),
                      "fused_pairs": work["fused_pairs"], "mean_series_terms": work["mean_ncoef"],
-                     "note": "algorithmic = 2 n^2 terms + 3 n^2 per fused (vector, branch) pair; "
-                             "executed = DMMA flops incl. 8-branch group and 104-column padding"},
+                     "note": "the FP64 tensor kernel of the level launches (branches above internal nodes); "
+                             "algorithmic = 2 n^2 terms + 3 n^2 per (vector, branch) pair it processes; "
+                             "executed_dmma = what a dense coefficient table would execute incl. 8-branch "
+                             "group and 104-column padding (the slot-prefix table skips about 38 % of it); "
+                             "observed-leaf branches of generator vectors are in roofline_leaf"},
+        "roofline_leaf": {"kernel": "leaf_lowp_kernel", "bound": "tensor (tf32, mma.sync) / issue",
+                          "pairs": work["lowp_pairs"],
+                          "achieved": (work["lowp_tf32_flops"] / leaf_s / 1e12) if (leaf_s > 0 and work["lowp_pairs"]) else None,
+                          "unit": "TFLOP/s (tf32)",
+                          "peak": peaks.get("bf16_tflops", 1590.0) / 2.0,
+                          "peak_source": "half of MEASURED_PEAKS.json bf16_tflops (dense TF32 runs at half the bf16 rate)",
+                          "frac": (work["lowp_tf32_flops"] / leaf_s / 1e12 / (peaks.get("bf16_tflops", 1590.0) / 2.0))
+                          if (leaf_s > 0 and work["lowp_pairs"]) else None,
+                          "fp64_column_gflops": (work["lowp_fp64_flops"] / leaf_s / 1e9) if leaf_s > 0 else None,
+                          "launch_ms": leaf_s / max(n_chunks, 1) * 1e3,
+                          "note": "observed-leaf branches of generator vectors: one column of P in FP64 plus the "
+                                  "floor correction of the row sum from the full matrix in TF32 (2 n * 104 * 8 ceil(terms/8) "
+                                  "flops per pair); the kernel is issue / latency bound, the fraction of the TF32 "
+                                  "tensor peak is reported for completeness"},
         "roofline_squaring": {"kernel": "taylor_apply_kernel<EVAL> + square_post_kernel", "bound": "tensor",
                               "achieved": list_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                               "frac": (list_tf / fp64_peak) if list_tf else None,

@@ -49,8 +49,24 @@ def pade_flops(n, s):
     return (2.0 * (6 + np.asarray(s, dtype=np.float64)) + 8.0 / 3.0) * float(n) ** 3
 
 
-def fused_work(flat, nu, mu, groups_per_warp=1):
+def is_generator_row(rows, n_states):
+    """Per parameter row (device order): True when every off-diagonal rate of Q is >= 0, i.e.
+    the vector takes the TF32 leaf path (n <= 104).  Mirrors CEVB_NORM_GENERATOR for ChromEvol
+    rate matrices: rates are r * (1 + linear_rate * i), i = 1..N."""
+    rows = np.atleast_2d(np.asarray(rows, dtype=np.float64))
+    N = n_states - 1
+    lin_ok = (1.0 + rows[:, 7] * 1.0 >= 0.0) & (1.0 + rows[:, 7] * N >= 0.0)
+    rates_ok = np.all(rows[:, :7] >= 0.0, axis=1) & np.all(np.isfinite(rows[:, :8]), axis=1)
+    some = np.any(rows[:, :7] > 0.0, axis=1)
+    return lin_ok & rates_ok & some & (n_states <= 104)
+
+
+def fused_work(flat, nu, mu, groups_per_warp=1, lowp_leaf=None):
     """Work of the fused path for parameter vectors with shifted norm nu[b] and shift mu[b].
+
+    ``lowp_leaf[b]`` (default: none): vectors whose observed-leaf branches go through
+    leaf_lowp_kernel (one FP64 column + the TF32 floor correction) instead of the FP64 tensor
+    kernel; their leaf pairs are accounted under "lowp_*", not under the FP64 figures.
 
     algorithmic flops per fused (vector, branch): 2 n^2 ncoef (the series contraction) + 3 n^2
     (floor/row sum/dot product); executed DMMA flops follow the kernel's grouping (a warp owns
@@ -66,11 +82,27 @@ def fused_work(flat, nu, mu, groups_per_warp=1):
     alg = dmma = 0.0
     n_fused = n_mat = n_ident = 0
     nc_sum = 0.0
-    for items in lists:                                   # one launch each, in this order
+    lowp_pairs = 0
+    lowp_tf32 = lowp_fp64 = 0.0
+    lowp_leaf = (np.zeros(nu.shape, dtype=bool) if lowp_leaf is None
+                 else np.asarray(lowp_leaf, dtype=bool))
+    for li, items in enumerate(lists):                    # one launch each, in this order
         if len(items) == 0:
             continue
         kind, nc, _ = plan_pairs(flat.dist_eff[items], nu, mu)
         fused, mat, ident = kind == 0, kind == 2, kind == 1
+        if li == 0 and lowp_leaf.any():
+            # leaf launch, generator vectors: 2 n terms for the FP64 column, 2 n * 104 * 8 ceil(terms/8)
+            # TF32 flops for the floor correction, per pair
+            lp = fused & lowp_leaf[:, None]
+            ncl = np.where(lp, nc, 0)
+            lowp_pairs += int(lp.sum())
+            lowp_fp64 += float(np.sum(2.0 * n * ncl))
+            lowp_tf32 += float(np.sum(lp * (2.0 * n * 104 * 8 * ((ncl + 7) // 8))))
+            n_mat += int((mat & lowp_leaf[:, None]).sum())
+            n_ident += int((ident & lowp_leaf[:, None]).sum())
+            keep = ~lowp_leaf
+            fused, mat, ident = fused & keep[:, None], mat & keep[:, None], ident & keep[:, None]
         nc = np.where(fused, nc, 0)
         kc = (nc + 3) // 4
         alg += float(np.sum(fused * (2.0 * n * n * nc + 3.0 * n * n)))
@@ -85,4 +117,5 @@ def fused_work(flat, nu, mu, groups_per_warp=1):
         nc_sum += float(nc[fused].sum())
     return {"algorithmic_flops": alg, "dmma_flops": dmma, "fused_pairs": n_fused,
             "materialised_pairs": n_mat, "identity_pairs": n_ident,
-            "mean_ncoef": nc_sum / max(n_fused, 1)}
+            "mean_ncoef": nc_sum / max(n_fused, 1),
+            "lowp_pairs": lowp_pairs, "lowp_tf32_flops": lowp_tf32, "lowp_fp64_flops": lowp_fp64}

@@ -1151,6 +1151,16 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const float4& a, 
           "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)));
 }
 
+// the first k-block of a row: D = A * B (no accumulator to clear beforehand)
+__device__ __forceinline__ void mma_tf32_16x8x8_first(float (&c)[4], const float4& a, const float2& b) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%10,%10,%10,%10};\n"
+        : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+        : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)),
+          "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)), "f"(0.0f));
+}
+
 constexpr int LP_MAXSTAGE = 4;
 
 __host__ __device__ inline size_t lowp_fixed_bytes(int nw, int n) {
@@ -1342,9 +1352,12 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : 2)
         mbar_wait_backoff(&full[s], par);
         const float2* Bq = reinterpret_cast<const float2*>(Bs + (size_t)s * stage_floats) + lane;
         float acc[F_JT][4];
+        {
+            const float4 af = Tw[0];
 #pragma unroll
-        for (int jt = 0; jt < F_JT; ++jt) acc[jt][0] = acc[jt][1] = acc[jt][2] = acc[jt][3] = 0.0f;
-        for (int kb = 0; kb < wk; ++kb) {
+            for (int jt = 0; jt < F_JT; ++jt) mma_tf32_16x8x8_first(acc[jt], af, Bq[jt * 32]);
+        }
+        for (int kb = 1; kb < wk; ++kb) {
             const float4 af = Tw[(size_t)kb * 32];
             const float2* Bk = Bq + (size_t)kb * F_JT * 32;
 #pragma unroll
@@ -1383,12 +1396,15 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : 2)
             }
         }
         // (3) corr = sum_j max(1e-12 - P_ij, 0) for rows g and g + 8 of the group
-        float c0 = -padfix, c1 = -padfix;
+        // as 26 * 1e-12 - sum_j min(P_ij, 1e-12) per lane: one min and one add per entry (FP32 keeps
+        // 1e-17 absolute on sums of this size)
+        float m0 = 0.0f, m1 = 0.0f;
 #pragma unroll
         for (int jt = 0; jt < F_JT; ++jt) {
-            c0 += fmaxf(1e-12f - acc[jt][0], 0.0f) + fmaxf(1e-12f - acc[jt][1], 0.0f);
-            c1 += fmaxf(1e-12f - acc[jt][2], 0.0f) + fmaxf(1e-12f - acc[jt][3], 0.0f);
+            m0 += fminf(acc[jt][0], 1e-12f) + fminf(acc[jt][1], 1e-12f);
+            m1 += fminf(acc[jt][2], 1e-12f) + fminf(acc[jt][3], 1e-12f);
         }
+        float c0 = (26.0f * 1e-12f - padfix) - m0, c1 = (26.0f * 1e-12f - padfix) - m1;
         c0 += __shfl_xor_sync(0xffffffffu, c0, 1);
         c0 += __shfl_xor_sync(0xffffffffu, c0, 2);
         c1 += __shfl_xor_sync(0xffffffffu, c1, 1);

@@ -315,7 +315,7 @@ class LikelihoodEngine:
             prune(0, 0, FUSED_INIT | leafvec)
             ev = self._mark("init", e2)
             prune(0, 0, FUSED_LEAVES)
-            ev = self._mark("apply", ev)
+            ev = self._mark("leaf", ev)
             for lv in range(f.n_levels):
                 prune(lv, lv + 1, FUSED_APPLY)
                 ev = self._mark("apply", ev)

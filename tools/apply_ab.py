@@ -33,11 +33,11 @@ for _ in range(R):
     for name, e0, e1 in eng.stage_events:
         ms = e0.elapsed_time(e1)
         tot[name] = tot.get(name, 0.0) + ms
+        if name == "leaf":
+            cur.append(ms)
+            first_apply.append(ms)
         if name == "apply":
             cur.append(ms)
-            if seen_apply == 0:
-                first_apply.append(ms)
-            seen_apply += 1
     per_launch = cur if per_launch is None else [a + b for a, b in zip(per_launch, cur)]
 eng.stage_events = None
 if os.environ.get("AB_LEVELS"):
@@ -59,5 +59,5 @@ e1.record()
 torch.cuda.synchronize()
 label = sys.argv[1] if len(sys.argv) > 1 else ""
 knobs = {k: v for k, v in os.environ.items() if k.startswith("CEVB_")}
-print(f"{label:14s} leaf {sum(first_apply) / R:7.3f} ms  apply {tot['apply'] / R:7.3f}  prepare {tot['prepare'] / R:6.3f}  "
+print(f"{label:14s} leaf {sum(first_apply) / R:7.3f} ms  apply {(tot['apply'] + tot.get('leaf', 0.0)) / R:7.3f}  prepare {tot['prepare'] / R:6.3f}  "
       f"expm {tot['expm'] / R:6.3f}  combine {tot['combine'] / R:6.3f}  step({NS} streams) {e0.elapsed_time(e1) / R:7.3f} ms  {knobs}")
