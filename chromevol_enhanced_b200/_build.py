@@ -15,7 +15,7 @@ import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(CSRC, "libcevb200.so")
-SOURCES = ["abi.cu", "prepare.cu", "expm.cu", "prune.cu", "fused.cu", "mapper.cu"]
+SOURCES = ["abi.cu", "prepare.cu", "expm.cu", "prune.cu", "reconstruct.cu", "fused.cu", "mapper.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "chromevol_b200.h")]
 
 NVCC_FLAGS = [

@@ -61,6 +61,13 @@ _PROTOTYPES = {
                               c_dp, c_dp, _c.c_void_p]),
     "cevb_argmax_states": (_c.c_int, [c_dp, _c.c_int, _c.c_int, _c.c_int, c_dp, c_dp, c_dp,
                                       _c.c_void_p]),
+    "cevb_marginal_down": (_c.c_int, [c_dp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, c_dp, c_dp, c_dp,
+                                      c_dp, c_dp, _c.POINTER(_c.c_int32), _c.c_int, c_dp, c_dp, c_dp,
+                                      c_dp, _c.c_void_p]),
+    "cevb_joint_reconstruct": (_c.c_int, [c_dp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                          c_dp, c_dp, _c.POINTER(_c.c_int32), _c.c_int, c_dp, c_dp,
+                                          c_dp, c_dp, c_dp, _c.c_int, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                          c_dp, _c.c_void_p]),
     "cevb_stoch_map": (_c.c_int, [c_dp, _c.c_int, c_dp, _c.c_int, c_dp, c_dp, c_dp, _c.c_int,
                                   _c.c_ulonglong, _c.c_longlong, _c.c_longlong, _c.c_int, c_dp, c_dp,
                                   c_dp, _c.c_longlong, c_dp, _c.c_void_p]),

@@ -355,6 +355,49 @@ class ChromEvolLikelihoodCalculator:
         return self.tree
 
 
+    # -- additive: true marginal and joint reconstruction ------------------------------------
+    # The reference's docstring (AR:274-295) describes the up-pass + down-pass marginal
+    # reconstruction and the joint reconstruction it does NOT implement; BASELINE.json's north
+    # star names both.  They are offered beside ``ancestral_state_reconstruction`` and never
+    # touch ``ml_count`` / ``ml_probability`` / ``state_probabilities`` (whose meaning stays the
+    # reference's arg max of the up-pass vector).  Parity: no reference implementation exists;
+    # the kernels are tested against oracle/reconstruction_oracle.py, which is pinned by
+    # exhaustive enumeration over the reference's transition matrices.
+    def _reconstruction_inputs(self):
+        if self._has_branch_params():
+            raise NotImplementedError("marginal / joint reconstruction use the model-wide "
+                                      "parameters; branch-specific sets are not supported here")
+        if self.root_frequencies is None:
+            self.set_root_frequencies(None)
+        eng = self._device_engine()
+        return eng, params_to_row(self.model.params), np.array(self.root_frequencies, dtype=np.float64)
+
+    def marginal_reconstruction(self):
+        """Posterior P(state of node | all tip data) for every node (Felsenstein up-pass followed
+        by a down-pass).  Annotates ``marginal_count``, ``marginal_probability`` and
+        ``marginal_probabilities`` on every node and returns the tree."""
+        eng, row, root = self._reconstruction_inputs()
+        post, _ = eng.marginal_reconstruction(row, root_freq=root)
+        post = post.cpu().numpy()
+        best = post.argmax(axis=1)
+        for k, node in enumerate(self._flat.nodes):
+            node.add_features(marginal_count=np.int64(best[k]))
+            node.add_features(marginal_probability=np.float64(post[k, best[k]]))
+            node.add_features(marginal_probabilities=post[k].copy())
+        return self.tree
+
+    def joint_reconstruction(self):
+        """The single most probable joint assignment of states to all nodes (Pupko et al. 2000:
+        max-product up-pass + backtrack).  Annotates ``joint_count`` on every node and returns
+        (tree, log P(assignment, data))."""
+        eng, row, root = self._reconstruction_inputs()
+        states, logp = eng.joint_reconstruction(row, root_freq=root)
+        states = states.cpu().numpy()
+        for k, node in enumerate(self._flat.nodes):
+            node.add_features(joint_count=np.int64(states[k]))
+        return self.tree, logp
+
+
 class ChromEvolOptimizer:
     """Negative log-likelihood objective + L-BFGS-B driver (AR:325-426)."""
 

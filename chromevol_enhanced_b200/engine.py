@@ -608,6 +608,72 @@ class LikelihoodEngine:
             self._het_ws = ws
         return ws
 
+    # ------------------------------------------------------------------ marginal / joint
+    # ADDITIVE calls (the reference has no down-pass and no joint backtrack, AR:283-295; its
+    # ml_count stays the arg max of the up-pass vector).  Both need every P(t), so they run on a
+    # materialised companion engine; one parameter vector per call.
+    def _materialised_companion(self):
+        if self.path == "materialised":
+            return self
+        eng = getattr(self, "_mat_engine", None)
+        if eng is None:
+            eng = LikelihoodEngine(self.flat, device=self.device, path="materialised", chunk=1)
+            self._mat_engine = eng
+        return eng
+
+    def _recon_tree_tensors(self):
+        if getattr(self, "d_parent", None) is None:
+            i32 = dict(dtype=torch.int32, device=self.device)
+            self.d_parent = torch.as_tensor(self.flat.parent, **i32)
+            self.d_depth_off = torch.as_tensor(self.flat.depth_off, **i32)
+            self.h_depth_off = np.ascontiguousarray(self.flat.depth_off, dtype=np.int32)
+
+    def marginal_reconstruction(self, params_row, root_freq=None):
+        """Posterior state probabilities of every node given ALL the data (up-pass + down-pass)
+        for one parameter vector -> (post (n_nodes, n) CUDA tensor, logL float)."""
+        eng = self._materialised_companion()
+        eng._recon_tree_tensors()
+        f = eng.flat
+        row = np.ascontiguousarray(np.asarray(params_row, dtype=np.float64).reshape(1, 9))
+        d_root = root_freq if torch.is_tensor(root_freq) else eng.root_freq_tensor(root_freq)
+        logl = eng.log_likelihood(row, root_freq=d_root)
+        f64 = dict(dtype=torch.float64, device=eng.device)
+        down = torch.empty((1, f.n_nodes, eng.ldp), **f64)
+        post = torch.empty((1, f.n_nodes, eng.ldp), **f64)
+        _lib.check(eng.lib.cevb_marginal_down(
+            _lib.ptr(eng._ws.P), 1, f.n_t, eng.n, f.n_nodes, _lib.ptr(eng.d_parent),
+            _lib.ptr(eng.d_child_off), _lib.ptr(eng.d_child_idx), _lib.ptr(eng.d_branch_of),
+            _lib.ptr(eng.d_leaf_code),
+            eng.h_depth_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), f.n_depths,
+            _lib.ptr(d_root), _lib.ptr(eng._node_vec), _lib.ptr(down), _lib.ptr(post),
+            _stream_ptr()), "cevb_marginal_down")
+        return post[0, :, :eng.n], float(logl[0])
+
+    def joint_reconstruction(self, params_row, root_freq=None):
+        """The single most probable joint assignment of states to all nodes (Pupko et al. 2000)
+        for one parameter vector -> (states (n_nodes,) int32 CUDA tensor, log P(states, data))."""
+        eng = self._materialised_companion()
+        eng._recon_tree_tensors()
+        f = eng.flat
+        row = np.ascontiguousarray(np.asarray(params_row, dtype=np.float64).reshape(1, 9))
+        d_root = root_freq if torch.is_tensor(root_freq) else eng.root_freq_tensor(root_freq)
+        eng.log_likelihood(row, root_freq=d_root)                   # fills P (and the up vectors)
+        dev = eng.device
+        lj = torch.zeros((1, f.n_nodes, eng.ldp), dtype=torch.float64, device=dev)
+        cj = torch.zeros((1, f.n_nodes, eng.n), dtype=torch.int32, device=dev)
+        expo = torch.zeros((1, f.n_nodes), dtype=torch.int64, device=dev)
+        states = torch.zeros((1, f.n_nodes), dtype=torch.int32, device=dev)
+        logp = torch.zeros(1, dtype=torch.float64, device=dev)
+        _lib.check(eng.lib.cevb_joint_reconstruct(
+            _lib.ptr(eng._ws.P), 1, f.n_t, eng.n, f.n_nodes, f.root, _lib.ptr(eng.d_parent),
+            _lib.ptr(eng.d_level_nodes),
+            eng.h_level_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), f.n_levels,
+            _lib.ptr(eng.d_child_off), _lib.ptr(eng.d_child_idx), _lib.ptr(eng.d_branch_of),
+            _lib.ptr(eng.d_leaf_code), _lib.ptr(eng.d_depth_off), f.n_depths, _lib.ptr(d_root),
+            _lib.ptr(lj), _lib.ptr(cj), _lib.ptr(expo), _lib.ptr(states), _lib.ptr(logp),
+            _stream_ptr()), "cevb_joint_reconstruct")
+        return states[0], float(logp[0])
+
     def node_vectors(self, which=0):
         """Conditional-likelihood vectors (n_nodes, n) of vector `which` of the last chunk."""
         return self._node_vec[which, :, :self.n]

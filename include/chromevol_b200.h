@@ -225,6 +225,34 @@ int cevb_prune(const double* P, int B, int E, int n, int n_nodes, int root,
 int cevb_argmax_states(const double* node_vec, int B, int n_nodes, int n, int32_t* ml_count,
                        double* ml_prob, double* probs, void* stream);
 
+/* ---- (4b) marginal and joint reconstruction -- ADDITIVE: the reference has neither (its
+ * ancestral_state_reconstruction, AR:274-322, documents the missing down-pass and takes the arg
+ * max of the up-pass vector = cevb_argmax_states).  BASELINE.json's north star names both; the
+ * CPU restatement is oracle/reconstruction_oracle.py, pinned by exhaustive enumeration over the
+ * reference's transition matrices (AR:136-166).  Both read materialised P [B][E][n][ldp] and the
+ * tree arrays of cevb_prune, plus
+ *   parent    [n_nodes]          parent of every node (-1 for the root),
+ *   depth_off [n_depths+1]       nodes are numbered in level order (root 0), so the nodes of
+ *                                depth d are the id range [depth_off[d], depth_off[d+1]).
+ * cevb_marginal_down: node_vec = the up-pass vectors (cevb_prune / cevb_prune_fused); down
+ * [B][n_nodes][ldp] is scratch, post [B][n_nodes][ldp] receives P(state of node | all data).
+ * depth_off is a HOST array here (one launch per depth). */
+int cevb_marginal_down(const double* P, int B, int E, int n, int n_nodes, const int32_t* parent,
+                       const int32_t* child_off, const int32_t* child_idx,
+                       const int32_t* branch_of, const int32_t* leaf_code,
+                       const int32_t* depth_off_host, int n_depths, const double* root_freq,
+                       const double* node_vec, double* down, double* post, void* stream);
+/* cevb_joint_reconstruct (Pupko et al. 2000): states [B][n_nodes] of the single most probable
+ * assignment, joint_logp [B] = log P(assignment, data).  Scratch: lj [B][n_nodes][ldp],
+ * cj [B][n_nodes][n] int32, expo [B][n_nodes] int64.  depth_off is a DEVICE array here. */
+int cevb_joint_reconstruct(const double* P, int B, int E, int n, int n_nodes, int root,
+                           const int32_t* parent, const int32_t* level_nodes,
+                           const int32_t* level_off_host, int n_levels, const int32_t* child_off,
+                           const int32_t* child_idx, const int32_t* branch_of,
+                           const int32_t* leaf_code, const int32_t* depth_off, int n_depths,
+                           const double* root_freq, double* lj, int32_t* cj, long long* expo,
+                           int32_t* states, double* joint_logp, void* stream);
+
 /* ---- (5) forward stochastic mapping: replaces StochasticMapper.perform_stochastic_mapping,
  * AR:523-576, with a counter-based Philox4x32-10 generator keyed by (seed, replicate, branch)
  * so any sharding of replicates gives the same histograms.

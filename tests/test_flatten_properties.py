@@ -97,7 +97,9 @@ def test_flat_tree_invariants(seed, n_leaves):
     assert all(f.dist_eff[a] >= f.dist_eff[b] for a, b in zip(leaf_list, leaf_list[1:]))
     for lv in range(f.n_levels):
         part = f.level_child[f.level_child_off[lv]:f.level_child_off[lv + 1]].tolist()
-        assert all(level_of[int(f.parent[c])] == lv for c in part)
+        # a branch is launched as soon as its child's vector exists (child height == list index),
+        # never after its parent is combined
+        assert all(f.height[c] == lv and level_of[int(f.parent[c])] >= lv for c in part)
         assert all(f.dist_eff[a] >= f.dist_eff[b] for a, b in zip(part, part[1:]))
     # pre-order for the simulator: parents before children, root first
     pos = {int(v): i for i, v in enumerate(f.preorder.tolist())}
