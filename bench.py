@@ -590,6 +590,35 @@ def run_other_configs(dev, rank, world, eng2, tree2, counts2):
                                                "one scalar back per call, node vectors stay on the device",
                                    "ms": wall * 1e3, "neg_logL": float(f)}
 
+    # ---- configs[1]: ancestral reconstruction of one parameter vector (1,000 taxa, N=100), rank 0:
+    # the reference's arg max of the up-pass vectors, and the additive marginal (down-pass) and
+    # joint (Pupko) reconstructions over materialised P
+    if rank == 0:
+        model = cev.ChromEvolutionModel(MAX_CHR)
+        calc = cev.ChromEvolLikelihoodCalculator(tree2, counts2, model)
+        calc.set_root_frequencies(np.ones(MAX_CHR + 1) / (MAX_CHR + 1))
+        rec = {}
+        for label, fn in (("argmax_up_pass", lambda: (calc.__setattr__("likelihoods", {}),
+                                                       calc.ancestral_state_reconstruction())),
+                          ("marginal_down_pass", calc.marginal_reconstruction),
+                          ("joint_pupko", calc.joint_reconstruction)):
+            fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            rec[label + "_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+        nodes = list(tree2.traverse())
+        rec["nodes_where_marginal_differs_from_up_pass_argmax"] = int(sum(
+            int(nd.marginal_count) != int(nd.ml_count) for nd in nodes if not nd.is_leaf()))
+        rec["nodes_where_joint_differs_from_marginal"] = int(sum(
+            int(nd.joint_count) != int(nd.marginal_count) for nd in nodes if not nd.is_leaf()))
+        rec["workload"] = ("BASELINE configs[1]: ancestral reconstruction of one parameter vector, 1,000 taxa, "
+                           "N=100, host wall clock incl. annotating the 1,999 nodes (marginal / joint: every "
+                           "P(t) materialised by the Pade kernel, then one launch per depth)")
+        out["reconstruction"] = rec
+
     # ---- the 9-point finite-difference step of one L-BFGS-B gradient, sharded over the ranks
     rows9 = np.tile(synthetic.default_param_row(), (9, 1))
     for k in range(8):

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import numpy as np
 
-KC = 12              # CEVB_TAYLOR_KC
+KC = 16              # CEVB_TAYLOR_KC
 TRUNC = 1e-18        # CEVB_TAYLOR_TRUNC
 
 

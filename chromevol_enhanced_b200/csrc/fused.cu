@@ -37,7 +37,8 @@
 
 namespace cevb {
 
-constexpr int F_KC = CEVB_TAYLOR_KC;       // chunks of 4 series coefficients (degrees 0..39)
+constexpr int F_KC = CEVB_TAYLOR_KC;       // chunks of 4 series coefficients (degrees 0..63)
+static_assert(F_KC <= 16 && F_KC % 2 == 0, "slot counts are 16 nibbles of one 64-bit word; TF32 k-blocks pair chunks");
 constexpr int F_JT = 13;                   // 8-column tiles per pass (104 columns)
 constexpr double F_TRUNC = CEVB_TAYLOR_TRUNC;  // truncation bound of the series (absolute, entries <= 1)
 
@@ -218,6 +219,9 @@ __global__ void __launch_bounds__(128) q_structure_kernel(const double* __restri
 // g, degree t).  `dense` != 0 hands every tile its slot at chunk 0 in natural order (identity
 // permutation, m(c) = all tiles): the layout without sparsity, kept for A/B measurements.
 constexpr int TCR = 4;                                   // rows of C_k per CTA
+// 1 / k for k = 1 .. 4 F_KC as the IEEE quotient 1.0 / k (filled by the host on first use): the
+// recurrence divides by k once per step and a double division costs ~20 instructions per thread
+__constant__ double c_inv_int[4 * CEVB_TAYLOR_KC + 1];
 constexpr int TC_MAXPASS = ((CEVB_MAX_N + 7) / 8 + F_JT - 1) / F_JT;
 
 __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restrict__ pw,
@@ -230,7 +234,13 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
     extern __shared__ double shc[];
     double* cur = shc;                    // [TCR][npad]
     double* nxt = shc + TCR * npad;       // [TCR][npad]
-    double* stg = shc + 2 * TCR * npad;   // [TCR][npad][4]
+    // staging of one chunk, DEGREE-major: [TCR][4 degrees][sst] with a row stride of npad + 4
+    // doubles, so that the per-degree store of a step (lane = column) and the TF32 read-out are
+    // conflict-free and the two degree rows a write-out lane pairs up sit 8 banks apart (the
+    // column-major [npad][4] layout cost 8 wavefronts per warp store: 126 M bank conflicts and
+    // 67 % LSU utilisation per 512-vector launch in the round-2 ncu capture)
+    double* stg = shc + 2 * TCR * npad;
+    const int sst = npad + 4;
     __shared__ uint8_t s_act[TCR][TC_MAXPASS * F_JT];     // tile holds a non-zero in this chunk
     __shared__ uint8_t s_perm[TCR][TC_MAXPASS][16];       // slot -> tile of the pass
     __shared__ int8_t s_slot[TCR][TC_MAXPASS][16];        // tile of the pass -> slot (-1: none yet)
@@ -248,6 +258,7 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
     const double nu_l = norms[(size_t)b * CEVB_NNORM + CEVB_NORM_SHIFTED];
     const bool lowp = lowp_on && npass == 1 && norms[(size_t)b * CEVB_NNORM + CEVB_NORM_GENERATOR] != 0.0;
     float* tfb = reinterpret_cast<float*>(tcb + taylor_meta_end_doubles(n));
+    const double inv_nu = 1.0 / nu_l;
     double scl = 1.0;          // k! / nu^k of the current degree
     double sc4[4] = {1.0, 1.0, 1.0, 1.0};
     // chunks any branch of this vector can need: the longest branch decides (all of them when
@@ -302,14 +313,14 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
     __syncthreads();
     for (int k = 0; k < k_end; ++k) {
         sc4[k & 3] = scl;
-        scl *= (double)(k + 1) / nu_l;
+        scl *= (double)(k + 1) * inv_nu;       // (TF32 copy only: the rounding of k!/nu^k is immaterial)
         for (int j = tid; j < npad; j += 128) {
 #pragma unroll
             for (int r = 0; r < TCR; ++r)
-                stg[(size_t)(r * npad + j) * 4 + (k & 3)] = (j < n) ? cur[r * npad + j] : 0.0;
+                stg[(size_t)(r * 4 + (k & 3)) * sst + j] = (j < n) ? cur[r * npad + j] : 0.0;
         }
         if (k + 1 < k_end) {
-            const double inv = 1.0 / (double)(k + 1);
+            const double inv = c_inv_int[k + 1];       // 1 / (k + 1), correctly rounded (host table)
             if (j0 < n) {
                 double acc[TCR];
 #pragma unroll
@@ -363,7 +374,7 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
 #pragma unroll
                     for (int d = 0; d < 4; ++d) {
                         // all 13 tiles are written: columns beyond npad are zeros
-                        const float v = tid < npad ? (float)(stg[((size_t)r * npad + tid) * 4 + d] * sc4[d]) : 0.0f;
+                        const float v = tid < npad ? (float)(stg[(size_t)(r * 4 + d) * sst + tid] * sc4[d]) : 0.0f;
                         uint32_t u;
                         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
                         dst[(g8 * 4 + d) * 2 + half] = __uint_as_float(u);
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
             // NaN counts as non-zero)
             for (int x = warp; x < TCR * nj; x += 4) {
                 const int r = x / nj, jt = x - r * nj;
-                const double v = stg[((size_t)r * npad + jt * 8) * 4 + lane];
+                const double v = stg[(size_t)(r * 4 + (lane >> 3)) * sst + jt * 8 + (lane & 7)];
                 const int any = __any_sync(0xffffffffu, !(v == 0.0));
                 if (lane == 0) s_act[r][jt] = (uint8_t)any;
             }
@@ -415,8 +426,9 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
                         double2 v = make_double2(0.0, 0.0);
                         if (sl < ns) {
                             const int jt = p * F_JT + s_perm[r][p][sl];
-                            v = *reinterpret_cast<const double2*>(
-                                stg + ((size_t)r * npad + jt * 8) * 4 + rem * 2);
+                            // rem = column * 2 + half: degrees 2 half and 2 half + 1 of the column
+                            const double* sp = stg + (size_t)(r * 4 + 2 * (rem & 1)) * sst + jt * 8 + (rem >> 1);
+                            v = make_double2(sp[0], sp[sst]);
                         }
                         dst[x] = v;
                     }
@@ -583,7 +595,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 constexpr int F_MAXSTAGE = 4;
 
 __host__ __device__ inline size_t apply_header_bytes(int eb) {
-    return (size_t)((16 * F_MAXSTAGE + 4 * (3 * eb + 4) + 127) / 128) * 128;
+    // barriers, child / code / terms (int), tau / e^{-mu tau} (double) per branch
+    return (size_t)((16 * F_MAXSTAGE + 4 * (3 * eb + 4) + 16 * eb + 127) / 128) * 128;
 }
 // shared memory of the apply kernel: header (barriers, per-branch ints), the meta data of the
 // CTA's items (16 bytes each), the t^k table A [eb/8][F_KC][32], the child vectors L [eb][ldl]
@@ -700,10 +713,12 @@ __global__ void __launch_bounds__(32 * (NW + (DIRECT ? 0 : 1)),
     int* s_child = reinterpret_cast<int*>(smraw + 16 * F_MAXSTAGE);
     int* s_code = s_child + EB;
     int* s_nc = s_code + EB;
+    double* s_tau = reinterpret_cast<double*>(s_nc + EB + (EB & 1) + 2);   // 8-byte aligned: EB is a multiple of 8
+    double* s_a0 = s_tau + EB;
     uint4* s_meta = reinterpret_cast<uint4*>(smraw + apply_header_bytes(EB));   // [rows][npass]
-    double* As = reinterpret_cast<double*>(smraw + apply_header_bytes(EB) + a.meta_bytes);  // [EB/8][F_KC][32]
-    double* Ls = As + (size_t)(EB / 8) * F_KC * 32;                           // [EB][ldl] (not LEAF)
-    double* Bs = Ls + (LEAF ? 0 : (size_t)EB * ldl);                          // ring of item tiles
+    // [EB/8][ck][32]: only the ck chunks this CTA's longest branch needs; the child vectors and
+    // the ring follow (the shared memory is sized for ck = F_KC, the ring takes what is left)
+    double* As = reinterpret_cast<double*>(smraw + apply_header_bytes(EB) + a.meta_bytes);
 
     if (MODE == APPLY_LEAF && a.skip_generators &&
         a.norms[(size_t)b * CEVB_NNORM + CEVB_NORM_GENERATOR] != 0.0)
@@ -764,12 +779,8 @@ __global__ void __launch_bounds__(32 * (NW + (DIRECT ? 0 : 1)),
         s_child[x] = child;
         s_code[x] = code;
         s_nc[x] = nc;
-        double* arow = As + (size_t)(x >> 3) * F_KC * 32 + (x & 7) * 4;
-        double p = a0;  // e^{-mu tau} tau^k
-        for (int k = 0; k < 4 * F_KC; ++k) {
-            arow[(k >> 2) * 32 + (k & 3)] = (k < nc) ? p : 0.0;
-            p *= tau;
-        }
+        s_tau[x] = tau;
+        s_a0[x] = a0;
     }
     __syncthreads();
 
@@ -790,20 +801,45 @@ __global__ void __launch_bounds__(32 * (NW + (DIRECT ? 0 : 1)),
     }
     if (ck == 0) return;  // nothing on the fused path in this CTA (uniform across the CTA)
 
-    const int stage_doubles = ck * F_CHUNK;
-    int ns = a.stage_doubles_cap / stage_doubles;
-    if (ns > F_MAXSTAGE) ns = F_MAXSTAGE;
-
-    if (!DIRECT) {
-        if (tid == 0) {
-            for (int s = 0; s < ns; ++s) {
-                mbar_init(&full[s], 1);
-                mbar_init(&empty[s], __popc(active));
-            }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    double* Ls = As + (size_t)(EB / 8) * ck * 32;                             // [EB][ldl] (not LEAF)
+    double* Bs = Ls + (LEAF ? 0 : (size_t)EB * ldl);                          // ring of item tiles
+    // A operand e^{-mu tau} tau^k of every branch, chunk-major per 8-branch group
+    for (int x = tid; x < EB; x += blockDim.x) {
+        const int nc = s_nc[x];
+        const double tau = s_tau[x];
+        double* arow = As + (size_t)(x >> 3) * ck * 32 + (x & 7) * 4;
+        double p = s_a0[x];  // e^{-mu tau} tau^k
+        for (int k = 0; k < 4 * ck; ++k) {
+            arow[(k >> 2) * 32 + (k & 3)] = (k < nc) ? p : 0.0;
+            p *= tau;
         }
-        __syncthreads();   // barriers initialised
     }
+
+    // Ring geometry (CTA-uniform).  A stage holds `cps` consecutive chunks of one item.  When the
+    // ring has room for at least two whole items a stage is one item (cps = ck); otherwise the
+    // item is streamed in parts of cps < ck chunks through two stages, so that the ring can be
+    // smaller than an item of 16 chunks (53 KB) and the narrow CTA shapes keep four (3 warps) or
+    // two (7 warps) CTAs per SM.  The accumulators simply keep adding across the parts.
+    const int cap_chunks = (a.stage_doubles_cap + (EB / 8) * (F_KC - ck) * 32) / F_CHUNK;
+    int cps = ck, ns = cap_chunks / ck;
+    if (DIRECT) {
+        ns = 1;
+    } else if (ns >= 2) {
+        if (ns > F_MAXSTAGE) ns = F_MAXSTAGE;
+    } else {
+        ns = 2;
+        cps = cap_chunks >> 1;      // >= 1: the launcher never hands out less than two chunks
+    }
+    const int stage_doubles = cps * F_CHUNK;
+
+    if (!DIRECT && tid == 0) {
+        for (int s = 0; s < ns; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], __popc(active));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();   // barriers initialised, A operand in place
 
     if (warp != NW && !LEAF) {
         // child vectors (one-hot / uniform / conditional-likelihood vector of an internal child),
@@ -848,32 +884,35 @@ __global__ void __launch_bounds__(32 * (NW + (DIRECT ? 0 : 1)),
             for (int pass = 0; pass < npass; ++pass) {
                 const uint4 mt = s_meta[(i - i_begin) * npass + pass];
                 const unsigned long long cnts = ((unsigned long long)mt.w << 32) | mt.z;
-                uint32_t total = 0;
-                for (int c = 0; c < ck; ++c) total += (uint32_t)((cnts >> (4 * c)) & 15ull);
-                if (use > 0) {
-                    const uint32_t par = (uint32_t)((use - 1) & 1);
-                    mbar_wait_backoff(&empty[s], par);
-                }
-                mbar_expect_tx(&full[s], total * 256u);
-                double* dst = Bs + (size_t)s * stage_doubles;
                 const double* src = tcb + (size_t)(i * npass + pass) * F_ITEM;
-                int c = 0;
-                while (c < ck) {
-                    const int c_start = c;
-                    uint32_t bytes = 0;
-                    while (c < ck) {
-                        const uint32_t m = (uint32_t)((cnts >> (4 * c)) & 15ull);
-                        bytes += m * 256u;
-                        ++c;
-                        if (m != (uint32_t)F_JT) break;
+                for (int cb = 0; cb < ck; cb += cps) {          // one stage per part of the item
+                    const int ce = min(ck, cb + cps);
+                    uint32_t total = 0;
+                    for (int c = cb; c < ce; ++c) total += (uint32_t)((cnts >> (4 * c)) & 15ull);
+                    if (use > 0) {
+                        const uint32_t par = (uint32_t)((use - 1) & 1);
+                        mbar_wait_backoff(&empty[s], par);
                     }
-                    if (bytes)
-                        bulk_g2s(dst + (size_t)c_start * F_CHUNK, src + (size_t)c_start * F_CHUNK, bytes,
-                                 &full[s]);
-                }
-                if (++s == ns) {
-                    s = 0;
-                    ++use;
+                    mbar_expect_tx(&full[s], total * 256u);
+                    double* dst = Bs + (size_t)s * stage_doubles;
+                    int c = cb;
+                    while (c < ce) {
+                        const int c_start = c;
+                        uint32_t bytes = 0;
+                        while (c < ce) {
+                            const uint32_t m = (uint32_t)((cnts >> (4 * c)) & 15ull);
+                            bytes += m * 256u;
+                            ++c;
+                            if (m != (uint32_t)F_JT) break;
+                        }
+                        if (bytes)
+                            bulk_g2s(dst + (size_t)(c_start - cb) * F_CHUNK, src + (size_t)c_start * F_CHUNK,
+                                     bytes, &full[s]);
+                    }
+                    if (++s == ns) {
+                        s = 0;
+                        ++use;
+                    }
                 }
             }
         }
@@ -917,7 +956,7 @@ __global__ void __launch_bounds__(32 * (NW + (DIRECT ? 0 : 1)),
     const bool mine = s_nc[xw] > 0;
     const int my_child = s_child[xw];
     const unsigned int row_off = (unsigned)my_child * (unsigned)a.ldp;   // n_nodes * ldp < 2^31
-    const double* Aw = As + (size_t)warp * F_KC * 32 + lane;
+    const double* Aw = As + (size_t)warp * ck * 32 + lane;
     const double* Lbase = Ls + (size_t)xw * ldl + 2 * t4;
     double rs0 = -padfix, rs1 = 0.0, dt0 = 0.0, dt1 = 0.0;
     bool have_prev = false;   // false only while the first item of the CTA is in flight
@@ -1000,7 +1039,7 @@ __global__ void __launch_bounds__(32 * (NW + (DIRECT ? 0 : 1)),
             uint32_t c_lo = mt.z, c_hi = mt.w;
             if (!DIRECT && !(CEVB_STUB & 2)) mbar_wait_backoff(&full[s], par);
             const double* Bq = DIRECT ? tcb + (size_t)(i * npass + pass) * F_ITEM + lane
-                                      : Bs + (size_t)s * stage_doubles + lane;
+                                      : Bs + (size_t)s * stage_doubles + lane;   // part 0 of the item
             // chunk 0 is interleaved with the epilogue of the previous item, so its DMMAs are
             // predicated per slot (SL < m(0)); the later chunks branch to the straight-line
             // variant of their slot count
@@ -1058,21 +1097,33 @@ __global__ void __launch_bounds__(32 * (NW + (DIRECT ? 0 : 1)),
                     else chunk0(std::integral_constant<int, 13>{});
                 }
             }
-            for (int c = 1; c < wk; ++c) {
-                c_lo = __funnelshift_r(c_lo, c_hi, 4);
-                c_hi >>= 4;
-                const int m = (int)(c_lo & 15u);
-                const double av = Aw[(size_t)c * 32];
-                const double* Bc = Bq + (size_t)c * F_CHUNK;
-                if (!(CEVB_STUB & 4)) chunk_dispatch<DIRECT>(m, acc, Bc, av);
-            }
-            // every shared-memory read of this stage has been consumed by an issued DMMA (the
-            // DMMAs are warp-wide, so all lanes' loads are complete)
-            if (!DIRECT) {
-                if (lane == 0 && !(CEVB_STUB & 2)) mbar_arrive(&empty[s]);
-                if (++s == ns) {
-                    s = 0;
-                    par ^= 1u;
+            // the remaining chunks, part by part (one part = one ring stage; a single part when
+            // the whole item fits a stage).  Every active consumer warp takes every stage of the
+            // item -- also the ones beyond its own wk chunks -- so the barrier counts stay fixed.
+            {
+                int c = 1, cbase = 0;
+                for (;;) {
+                    const int c_stop = min(wk, cbase + cps);
+                    for (; c < c_stop; ++c) {
+                        c_lo = __funnelshift_r(c_lo, c_hi, 4);
+                        c_hi >>= 4;
+                        const int m = (int)(c_lo & 15u);
+                        const double av = Aw[(size_t)c * 32];
+                        const double* Bc = Bq + (size_t)(c - cbase) * F_CHUNK;
+                        if (!(CEVB_STUB & 4)) chunk_dispatch<DIRECT>(m, acc, Bc, av);
+                    }
+                    if (DIRECT) break;
+                    // every shared-memory read of this stage has been consumed by an issued DMMA
+                    // (the DMMAs are warp-wide, so all lanes' loads are complete)
+                    if (lane == 0 && !(CEVB_STUB & 2)) mbar_arrive(&empty[s]);
+                    if (++s == ns) {
+                        s = 0;
+                        par ^= 1u;
+                    }
+                    cbase += cps;
+                    if (cbase >= ck) break;          // CTA-uniform
+                    if (!(CEVB_STUB & 2)) mbar_wait_backoff(&full[s], par);
+                    Bq = Bs + (size_t)s * stage_doubles + lane;
                 }
             }
             if (ONEPASS || pass_prev == npass - 1) finish_row(i_prev, have_prev);
@@ -1165,7 +1216,7 @@ constexpr int LP_MAXSTAGE = 4;
 
 __host__ __device__ inline size_t lowp_fixed_bytes(int nw, int n) {
     const int eb = nw * 16;
-    size_t b = 16 * LP_MAXSTAGE + 4 * (3 * eb + 4);            // barriers, child / code / terms
+    size_t b = 16 * LP_MAXSTAGE + 4 * (3 * eb + 4) + 16 * eb;  // barriers, child / code / terms, tau / a0
     b = (b + 127) / 128 * 128;
     b += (size_t)((16 * n + 127) / 128) * 128;                 // per-row meta (inv, counts)
     b += sizeof(double) * (size_t)(eb / 8) * F_KC * 32;        // FP64 t^k table (column dot product)
@@ -1194,14 +1245,14 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : 2)
     int* s_child = reinterpret_cast<int*>(smraw + 16 * LP_MAXSTAGE);
     int* s_code = s_child + EB;
     int* s_nc = s_code + EB;
-    size_t off = (16 * LP_MAXSTAGE + 4 * (3 * EB + 4) + 127) / 128 * 128;
+    double* s_tau = reinterpret_cast<double*>(s_nc + EB + 2);                   // 8-byte aligned
+    double* s_a0 = s_tau + EB;
+    size_t off = (16 * LP_MAXSTAGE + 4 * (3 * EB + 4) + 16 * EB + 127) / 128 * 128;
     uint4* s_meta = reinterpret_cast<uint4*>(smraw + off);
     off += (size_t)((16 * n + 127) / 128) * 128;
-    double* As = reinterpret_cast<double*>(smraw + off);                       // [EB/8][F_KC][32]
-    off += sizeof(double) * (size_t)(EB / 8) * F_KC * 32;
-    float* Tf = reinterpret_cast<float*>(smraw + off);                          // [NW][L_KB][32][4]
-    off += sizeof(float) * (size_t)NW * L_KB * 32 * 4;
-    float* Bs = reinterpret_cast<float*>(smraw + off);                          // ring
+    // the FP64 t^k table [EB/8][2 ck][32], the TF32 A fragments [NW][ck][32][4] and the ring follow;
+    // they are laid out once ck (the k-blocks this CTA's longest branch needs) is known
+    unsigned char* dyn = smraw + off;
 
     const double* tcb = a.tc + (size_t)b * taylor_vec_doubles(n);
     const float* tfb = reinterpret_cast<const float*>(tcb + taylor_meta_end_doubles(n));
@@ -1215,8 +1266,6 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : 2)
             s_meta[x] = make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
         }
     }
-    for (int x = tid; x < NW * L_KB * 32 * 4; x += blockDim.x) Tf[x] = 0.0f;
-    __syncthreads();
     for (int x = tid; x < EB; x += blockDim.x) {
         const int e = e0 + x;
         int nc = 0, child = -1, code = -2;
@@ -1237,25 +1286,8 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : 2)
         s_child[x] = child;
         s_code[x] = code;
         s_nc[x] = nc;
-        double* arow = As + (size_t)(x >> 3) * F_KC * 32 + (x & 7) * 4;
-        // A fragment of mma.m16n8k8 (row-major 16 x 8): lane 4g+t holds (row g, k t), (row g+8, k t),
-        // (row g, k t+4), (row g+8, k t+4)
-        float* trow = Tf + (size_t)(x >> 4) * L_KB * 128;
-        const int r16 = x & 15, gg = r16 & 7, hi = r16 >> 3;
-        double p = a0;        // e^{-mu tau} tau^k
-        double fk = 1.0;      // nu^k / k!
-        for (int k = 0; k < 4 * F_KC; ++k) {
-            arow[(k >> 2) * 32 + (k & 3)] = (k < nc) ? p : 0.0;
-            if (k < nc) {
-                const float v = (float)(p * fk);
-                uint32_t u;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-                const int kk = k & 7;
-                trow[((k >> 3) * 32 + gg * 4 + (kk & 3)) * 4 + hi + 2 * (kk >> 2)] = __uint_as_float(u);
-            }
-            p *= tau;
-            fk *= nu / (double)(k + 1);
-        }
+        s_tau[x] = tau;
+        s_a0[x] = a0;
     }
     __syncthreads();
 
@@ -1274,9 +1306,47 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : 2)
         active |= __shfl_xor_sync(0xffffffffu, active, o);
     }
     if (ck == 0) return;
-    const int stage_floats = ck * F_JT * L_TILE;
-    int ns = a.ring_floats / stage_floats;
-    if (ns > LP_MAXSTAGE) ns = LP_MAXSTAGE;
+    const int ck4 = 2 * ck;                                                     // 4-degree chunks
+    double* As = reinterpret_cast<double*>(dyn);                                // [EB/8][ck4][32]
+    float* Tf = reinterpret_cast<float*>(As + (size_t)(EB / 8) * ck4 * 32);     // [NW][ck][32][4]
+    float* Bs = Tf + (size_t)NW * ck * 128;                                     // ring
+    for (int x = tid; x < NW * ck * 128; x += blockDim.x) Tf[x] = 0.0f;
+    __syncthreads();
+    for (int x = tid; x < EB; x += blockDim.x) {
+        const int nc = s_nc[x];
+        const double tau = s_tau[x];
+        double* arow = As + (size_t)(x >> 3) * ck4 * 32 + (x & 7) * 4;
+        // A fragment of mma.m16n8k8 (row-major 16 x 8): lane 4g+t holds (row g, k t), (row g+8, k t),
+        // (row g, k t+4), (row g+8, k t+4)
+        float* trow = Tf + (size_t)(x >> 4) * ck * 128;
+        const int r16 = x & 15, gg = r16 & 7, hi = r16 >> 3;
+        double p = s_a0[x];   // e^{-mu tau} tau^k
+        double fk = 1.0;      // nu^k / k!
+        for (int k = 0; k < 4 * ck4; ++k) {
+            arow[(k >> 2) * 32 + (k & 3)] = (k < nc) ? p : 0.0;
+            if (k < nc) {
+                const float v = (float)(p * fk);
+                uint32_t u;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+                const int kk = k & 7;
+                trow[((k >> 3) * 32 + gg * 4 + (kk & 3)) * 4 + hi + 2 * (kk >> 2)] = __uint_as_float(u);
+            }
+            p *= tau;
+            fk *= nu / (double)(k + 1);
+        }
+    }
+    // ring geometry as in taylor_apply_kernel: whole rows when two of them fit, otherwise a row is
+    // streamed in parts of cps k-blocks through two stages.  The ring also takes the room the
+    // two tables above leave (the shared memory is sized for ck = L_KB).
+    const int cap_kb = (a.ring_floats + (L_KB - ck) * ((EB / 8) * 2 * 32 * 2 + NW * 128)) / (F_JT * L_TILE);
+    int cps = ck, ns = cap_kb / ck;
+    if (ns >= 2) {
+        if (ns > LP_MAXSTAGE) ns = LP_MAXSTAGE;
+    } else {
+        ns = 2;
+        cps = cap_kb >> 1;
+    }
+    const int stage_floats = cps * F_JT * L_TILE;
     if (tid == 0) {
         for (int s = 0; s < ns; ++s) {
             mbar_init(&full[s], 1);
@@ -1289,14 +1359,17 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : 2)
     if (warp == NW) {
         if (lane != 0) return;
         int s = 0, use = 0;
-        const uint32_t bytes = (uint32_t)stage_floats * sizeof(float);
         for (int i = i_begin; i < i_end; ++i) {
-            if (use > 0) mbar_wait_backoff(&empty[s], (uint32_t)((use - 1) & 1));
-            mbar_expect_tx(&full[s], bytes);
-            bulk_g2s(Bs + (size_t)s * stage_floats, tfb + (size_t)i * L_ROW, bytes, &full[s]);
-            if (++s == ns) {
-                s = 0;
-                ++use;
+            for (int cb = 0; cb < ck; cb += cps) {
+                const uint32_t bytes = (uint32_t)(min(ck, cb + cps) - cb) * F_JT * L_TILE * sizeof(float);
+                if (use > 0) mbar_wait_backoff(&empty[s], (uint32_t)((use - 1) & 1));
+                mbar_expect_tx(&full[s], bytes);
+                bulk_g2s(Bs + (size_t)s * stage_floats, tfb + (size_t)i * L_ROW + (size_t)cb * F_JT * L_TILE,
+                         bytes, &full[s]);
+                if (++s == ns) {
+                    s = 0;
+                    ++use;
+                }
             }
         }
         return;
@@ -1310,7 +1383,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : 2)
     const int q_kc = (s_nc[xq] + 3) >> 2;              // its 4-degree chunks
     const bool q_ok = q_child >= 0 && q_kc > 0 && q_code >= 0;
     const int q_tile = q_ok ? (q_code >> 3) : 0, q_col = q_code & 7;
-    const double* q_T = As + (size_t)(xq >> 3) * F_KC * 32 + (xq & 7) * 4;
+    const double* q_T = As + (size_t)(xq >> 3) * ck4 * 32 + (xq & 7) * 4;
     const size_t vb = (size_t)b * a.n_nodes * a.ldp;
     // columns >= n of the last tile hold zeros: they count 1e-12 each and are taken out again
     float padfix;
@@ -1319,7 +1392,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : 2)
         for (int j = 2 * t4; j < F_JT * 8; j += 8) cnt += (j >= n) + (j + 1 >= n);
         padfix = (float)cnt * 1e-12f;
     }
-    const float4* Tw = reinterpret_cast<const float4*>(Tf) + (size_t)warp * L_KB * 32 + lane;
+    const float4* Tw = reinterpret_cast<const float4*>(Tf) + (size_t)warp * ck * 32 + lane;
     int s = 0;
     uint32_t par = 0;
     for (int i = i_begin; i < i_end; ++i) {
@@ -1357,16 +1430,26 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW >= 15 ? 1 : 2)
 #pragma unroll
             for (int jt = 0; jt < F_JT; ++jt) mma_tf32_16x8x8_first(acc[jt], af, Bq[jt * 32]);
         }
-        for (int kb = 1; kb < wk; ++kb) {
-            const float4 af = Tw[(size_t)kb * 32];
-            const float2* Bk = Bq + (size_t)kb * F_JT * 32;
+        {
+            int kb = 1, kbase = 0;
+            for (;;) {
+                const int k_stop = min(wk, kbase + cps);
+                for (; kb < k_stop; ++kb) {
+                    const float4 af = Tw[(size_t)kb * 32];
+                    const float2* Bk = Bq + (size_t)(kb - kbase) * F_JT * 32;
 #pragma unroll
-            for (int jt = 0; jt < F_JT; ++jt) mma_tf32_16x8x8(acc[jt], af, Bk[jt * 32]);
-        }
-        if (lane == 0) mbar_arrive(&empty[s]);
-        if (++s == ns) {
-            s = 0;
-            par ^= 1u;
+                    for (int jt = 0; jt < F_JT; ++jt) mma_tf32_16x8x8(acc[jt], af, Bk[jt * 32]);
+                }
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (++s == ns) {
+                    s = 0;
+                    par ^= 1u;
+                }
+                kbase += cps;
+                if (kbase >= ck) break;           // CTA-uniform: every warp takes every stage
+                mbar_wait_backoff(&full[s], par);
+                Bq = reinterpret_cast<const float2*>(Bs + (size_t)s * stage_floats) + lane;
+            }
         }
         // (1b) the column dot product from the loads issued above (and the rare later chunks)
 #pragma unroll
@@ -1723,7 +1806,7 @@ static int fused_query() {
 //   CEVB_TW / CEVB_TM / CEVB_TS   branch-count thresholds of the CTA shapes (launch_apply_shapes)
 //   CEVB_DENSE=1                  coefficient table without the sparse slot order (A/B runs)
 struct Tuning {
-    int tw, tm, ts, td, dense, skew, ring_small, ring_medium, lowp;
+    int tw, tm, ts, td, dense, skew, ring_small, ring_medium, ring_wide, ring_lowp, lowp;
 };
 static const Tuning& tuning() {
     static const Tuning t = [] {
@@ -1732,14 +1815,17 @@ static const Tuning& tuning() {
             return v ? atoi(v) : dflt;
         };
         Tuning x;
-        x.tw = env("CEVB_TW", 160);   // wide: 15 consumer warps
+        x.tw = env("CEVB_TW", 200);   // wide: 15 consumer warps (one 512-thread CTA per SM: slower per launch from 200 branches down, and it keeps the other stream slices off the SM)
         x.tm = env("CEVB_TM", 100);   // medium: 7
         x.ts = env("CEVB_TS", 8);     // small: 3, else 1
         x.td = env("CEVB_TD", 16);    // at most this many branches: the ring-less variant
         x.dense = env("CEVB_DENSE", 0);
         x.skew = env("CEVB_SKEW", 0);
-        x.ring_small = env("CEVB_RING_S", 1);    // ring size of the 1- and 3-warp shapes, in full items
-        x.ring_medium = env("CEVB_RING_M", 1);   // ... of the 7-warp shape
+        x.ring_small = env("CEVB_RING_S", 16);   // most chunk slots in the ring of the 1- and 3-warp shapes
+        x.ring_medium = env("CEVB_RING_M", 16);  // ... of the 7-warp shape
+        x.ring_wide = env("CEVB_RING_W", F_MAXSTAGE * F_KC);   // ... of the 15-warp shape
+        x.ring_lowp = env("CEVB_RING_L", LP_MAXSTAGE * L_KB);  // k-block slots of leaf_lowp_kernel
+        // (small values force the multi-part streaming of an item: tests/test_gpu_ring_parts.py)
         x.lowp = env("CEVB_LOWP", 1);            // TF32 floor correction for the leaf launch
         return x;
     }();
@@ -1763,12 +1849,21 @@ static int launch_apply_one(ApplyArgs& a, int B, cudaStream_t st) {
     a.meta_bytes = (int)apply_meta_bytes(a.rows_per_cta * a.npass);
     const size_t fixed = apply_fixed_bytes(EB, MODE != APPLY_GENERAL ? 0 : a.ldl,
                                            a.rows_per_cta * a.npass);
-    const size_t one_stage = sizeof(double) * (size_t)F_ITEM;
-    if (fixed + one_stage > g_f_optin) return 1;  // does not fit: caller tries a smaller variant
-    size_t ring = g_f_optin - fixed;
-    // narrow CTAs: a smaller ring, more of them per SM
-    size_t ring_max = (NW >= 15 ? F_MAXSTAGE : (NW == 7 ? tuning().ring_medium : tuning().ring_small)) * one_stage;
-    if (ring > ring_max) ring = ring_max;
+    // Ring: as many chunk slots as fit beside the fixed part when the SM holds the CTAs its shape
+    // is meant for (15 warps: 1, 7: 2, 3 and 1: 4); fewer CTAs per SM when the child vectors of a
+    // large n leave no room.  At least two chunks (the kernel streams an item in parts).
+    const size_t one_chunk = sizeof(double) * (size_t)F_CHUNK;
+    const int ring_cap = NW >= 15 ? tuning().ring_wide : (NW == 7 ? tuning().ring_medium : tuning().ring_small);
+    size_t ring = 0;
+    for (int per_sm = (NW >= 15 ? 1 : (NW == 7 ? 2 : 4)); per_sm >= 1 && ring == 0; --per_sm) {
+        const size_t budget = g_f_optin / per_sm - (per_sm > 1 ? 1024 : 0);
+        if (budget < fixed + 2 * one_chunk) continue;
+        size_t chunks = (budget - fixed) / one_chunk;
+        if (chunks > (size_t)ring_cap) chunks = (size_t)ring_cap;
+        if (per_sm > 1 && chunks < 4) continue;      // too shallow a ring: fewer CTAs per SM
+        ring = chunks * one_chunk;
+    }
+    if (ring == 0) return 1;  // does not fit: caller tries a smaller variant
     a.stage_doubles_cap = (int)(ring / sizeof(double));
     a.skew = tuning().skew;
     const size_t smem = fixed + ring;
@@ -2070,10 +2165,13 @@ static int launch_leaf_lowp(const ApplyArgs& src, int B, cudaStream_t st) {
     ry = (a.n + rows_per_cta - 1) / rows_per_cta;
     const size_t fixed = lowp_fixed_bytes(NW, a.n);
     const size_t one_stage = sizeof(float) * (size_t)L_ROW;
+    const size_t one_kb = sizeof(float) * (size_t)F_JT * L_TILE;
     const size_t budget = g_f_optin / 2 - 2048;               // two CTAs per SM (1 KB reserved each)
-    if (fixed + one_stage > budget) return 1;
-    size_t ring = budget - fixed;
+    if (fixed + 2 * one_kb > budget) return 1;
+    size_t ring = (budget - fixed) / one_kb * one_kb;
     if (ring > LP_MAXSTAGE * one_stage) ring = LP_MAXSTAGE * one_stage;
+    if (ring > (size_t)tuning().ring_lowp * one_kb) ring = (size_t)tuning().ring_lowp * one_kb;
+    if (ring < 2 * one_kb) ring = 2 * one_kb;
     a.ring_floats = (int)(ring / sizeof(float));
     const size_t smem = fixed + ring;
     static size_t attr_smem = 0;
@@ -2151,8 +2249,16 @@ extern "C" int cevb_taylor_prepare(const double* pw, int B, int n, double t_max,
     const int npad = round_up(n, 8);
     q_structure_kernel<<<B, 128, 0, st>>>(pw, n, ldq_of(n), norms, csc, csc_cnt);
     CEVB_CHECK_LAUNCH("q_structure_kernel");
+    static bool inv_ready = false;
+    if (!inv_ready) {
+        double h[4 * CEVB_TAYLOR_KC + 1];
+        h[0] = 0.0;
+        for (int k = 1; k <= 4 * CEVB_TAYLOR_KC; ++k) h[k] = 1.0 / (double)k;
+        CEVB_CHECK_CUDA(cudaMemcpyToSymbol(c_inv_int, h, sizeof(h)));
+        inv_ready = true;
+    }
     dim3 grid((n + TCR - 1) / TCR, B);
-    const size_t csm = sizeof(double) * 6 * TCR * (size_t)npad;
+    const size_t csm = sizeof(double) * (2 * TCR * (size_t)npad + 4 * TCR * (size_t)(npad + 4));
     static size_t coeff_attr = 0;
     if (csm > coeff_attr) {
         CEVB_CHECK_CUDA(cudaFuncSetAttribute(taylor_coeff_kernel,

@@ -45,7 +45,7 @@ extern "C" {
 #define CEVB_MAX_SPARSE 12
 #define CEVB_NEVENT 8
 #define CEVB_MAX_N 288           /* largest supported matrix order (states 0..287) */
-#define CEVB_TAYLOR_KC 12       /* chunks of 4 series coefficients kept per vector: degrees 0..47 */
+#define CEVB_TAYLOR_KC 16       /* chunks of 4 series coefficients kept per vector: degrees 0..63 (16 = the nibbles of the 64-bit slot-count word) */
 #define CEVB_TAYLOR_TRUNC 1e-18 /* absolute truncation bound of the series.  Two orders below the
                                    unit roundoff on purpose: likelihoods of improbable data are
                                    sums of entries near the 1e-12 floor, and logL parity at 1e-9
@@ -129,8 +129,8 @@ int cevb_expm_branches_list(const double* pw, const double* norms, const uint16_
  *   doubles per vector); chunk c of row i holds degrees 4c..4c+3 interleaved per column.
  * The number of terms for a pair is the smallest K + 1 with
  *     x^(K+1)/(K+1)! / (1 - x/(K+2)) e^{-mu t} <= CEVB_TAYLOR_TRUNC,  x = nu t;
- * cevb_expm_plan lists every (vector, branch length) pair for which 4 * CEVB_TAYLOR_KC = 48 terms do not
- * reach that (nu t above about 9.5), which needs scaling and squaring and therefore a materialised
+ * cevb_expm_plan lists every (vector, branch length) pair for which 4 * CEVB_TAYLOR_KC = 64 terms do not
+ * reach that (nu t above about 15.6), which needs scaling and squaring and therefore a materialised
  * matrix: slot [B][E] = position in worklist (-1 = fused path, -2 = list overflow),
  * work_s [cap] = squarings of that position (may be NULL), *count = pairs found (may exceed
  * cap; the caller then re-plans).  It also records the decision per pair for the kernels:

@@ -115,16 +115,17 @@ def test_fused_general_variant_on_one_hot_children():
 
 
 def test_fused_p_sweep_up_to_the_switch_over():
-    """Series length selection: x = nu t swept from 1e-6 up to where 48 terms stop sufficing."""
+    """Series length selection: x = nu t swept from 1e-6 up to where 64 terms stop sufficing."""
     from chromevol_enhanced_b200 import synthetic
     row = synthetic.default_param_row()
     row[:5] = [2.0, 1.5, 0.7, 0.4, 0.3]
     Q = O.build_q(synthetic.row_to_dict(row), 100)
     _, _, _, nu, mu = _host_plan(Q, np.array([1.0]))
-    xs = np.array([1e-6, 1e-3, 0.05, 0.3, 0.9, 1.7, 2.5, 3.3, 4.1, 4.9, 5.7, 6.5, 7.5, 8.5, 9.3, 10.5, 13.0])
+    xs = np.array([1e-6, 1e-3, 0.05, 0.3, 0.9, 1.7, 2.5, 3.3, 4.1, 4.9, 5.7, 6.5, 7.5, 8.5, 9.3, 10.5, 13.0,
+                   14.5, 15.4, 17.0, 24.0])
     times = xs / nu
     kind, nc, sq, _, _ = _host_plan(Q, times)
-    assert kind[0] == 0 and kind[-1] == 2 and nc[kind == 0].max() >= 44
+    assert kind[0] == 0 and kind[-1] == 2 and nc[kind == 0].max() >= 60
     w, mode, _ = _apply(row, times, 100)
     for e, t in enumerate(times):
         assert (mode[0, e] == kind[e]).all()
@@ -244,7 +245,7 @@ def test_series_squaring_matrices_match_oracle(N):
     rows = synthetic.random_param_rows(8, seed=4, linear='positive')
     rows[:, :5] *= 4.0
     rows[1, 8] = 5
-    times = np.array([0.0, 1e-4, 0.011, 0.06, 0.2, 0.758285, 3.0])
+    times = np.array([0.0, 1e-4, 0.011, 0.06, 0.2, 0.45, 0.758285, 1.4, 3.0])
     P, slot, sq, n_nan = _series_matrices(rows, times, N)
     assert n_nan == 0
     n_checked = 0
@@ -361,7 +362,7 @@ def test_fused_worklist_overflow_is_redone():
     tree = synthetic.random_tree(80, seed=12, mean_len=0.3)
     counts = synthetic.simulate_tip_counts(tree, 40, seed=13)
     rows = synthetic.random_param_rows(12, seed=14, linear='positive')
-    rows[:, :5] *= 3.0
+    rows[:, :5] *= 10.0                     # nu t beyond the 64-term series on most branches
     flat = FlatTree(tree, counts, 40)
     # workspace so small that only one vector's worth of matrices fits
     fused = LikelihoodEngine(flat, path="fused", chunk=6, max_workspace_bytes=1 << 20)

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 def _calc(tree, data, max_chr, **over):
     from chromevol_enhanced_b200 import ChromEvolutionModel, ChromEvolLikelihoodCalculator
     model = ChromEvolutionModel(max_chr)
-    model.set_parameters(O.default_params(**over))
+    model.set_parameters(**O.default_params(**over))
     return ChromEvolLikelihoodCalculator(tree, data, model)
 
 
