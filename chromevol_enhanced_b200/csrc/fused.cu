@@ -144,7 +144,7 @@ __host__ __device__ inline PairPlan plan_pair(double t, double nu, double mu) {
 __global__ void __launch_bounds__(128) q_structure_kernel(const double* __restrict__ pw, int n,
                                                           int ldq, double* __restrict__ norms,
                                                           uint16_t* __restrict__ csc,
-                                                          uint8_t* __restrict__ csc_cnt) {
+                                                          uint8_t* __restrict__ csc_cnt, double t_max) {
     __shared__ double red[4];
     const int b = blockIdx.x, tid = threadIdx.x;
     const double* Q = pw + (size_t)b * CEVB_NPOW * n * ldq;
@@ -209,6 +209,15 @@ __global__ void __launch_bounds__(128) q_structure_kernel(const double* __restri
         out[CEVB_NORM_SHIFT] = anynan ? NAN : mu;
         out[CEVB_NORM_SHIFTED] = anynan ? NAN : nu;
         out[CEVB_NORM_GENERATOR] = (!anynan && !anyneg && nu > 0.0 && nu < INFINITY) ? 1.0 : 0.0;
+        // chunks any branch of this vector can need: the longest branch decides (all of them when
+        // it has to be scaled and squared, or when the caller gives no bound).  Decided once per
+        // vector here -- the series-length rule is a 64-step scalar loop with a division per step
+        int kc_need = F_KC;
+        if (t_max > 0.0) {
+            const PairPlan pp = plan_pair(t_max, anynan ? NAN : nu, anynan ? NAN : mu);
+            if (pp.kind == 0) kc_need = (pp.nc + 3) >> 2;
+        }
+        out[CEVB_NORM_CHUNKS] = (double)kc_need;
     }
 }
 
@@ -232,8 +241,8 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
                                                            int dense, int lowp_on,
                                                            double* __restrict__ tc) {
     extern __shared__ double shc[];
-    double* cur = shc;                    // [TCR][npad]
-    double* nxt = shc + TCR * npad;       // [TCR][npad]
+    double* cur = shc;                    // [npad][TCR]: the TCR rows of one column side by side
+    double* nxt = shc + TCR * npad;       // [npad][TCR]
     // staging of one chunk, DEGREE-major: [TCR][4 degrees][sst] with a row stride of npad + 4
     // doubles, so that the per-degree store of a step (lane = column) and the TF32 read-out are
     // conflict-free and the two degree rows a write-out lane pairs up sit 8 banks apart (the
@@ -261,13 +270,8 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
     const double inv_nu = 1.0 / nu_l;
     double scl = 1.0;          // k! / nu^k of the current degree
     double sc4[4] = {1.0, 1.0, 1.0, 1.0};
-    // chunks any branch of this vector can need: the longest branch decides (all of them when
-    // it has to be scaled and squared, or when the caller gives no bound)
-    int kc_need = F_KC;
-    if (t_max > 0.0) {
-        const PairPlan pp = plan_pair(t_max, norms[(size_t)b * CEVB_NNORM + CEVB_NORM_SHIFTED], mu);
-        if (pp.kind == 0) kc_need = (pp.nc + 3) >> 2;
-    }
+    // chunks any branch of this vector can need (q_structure_kernel decides from the longest branch)
+    const int kc_need = (int)norms[(size_t)b * CEVB_NNORM + CEVB_NORM_CHUNKS];
     const int k_end = 4 * kc_need;
     // The sparse column of (Q + mu I) a thread multiplies with is the same for every row and
     // all 39 steps: it is kept in registers (<= 12 entries), so a step is shared-memory loads
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
     }
     for (int j = tid; j < npad; j += 128) {
 #pragma unroll
-        for (int r = 0; r < TCR; ++r) cur[r * npad + j] = (j == i0 + r) ? 1.0 : 0.0;
+        for (int r = 0; r < TCR; ++r) cur[(j) * TCR + r] = (j == i0 + r) ? 1.0 : 0.0;
     }
     if (tid < TCR * TC_MAXPASS) {
         const int r = tid / TC_MAXPASS, p = tid - r * TC_MAXPASS;
@@ -317,47 +321,52 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
         for (int j = tid; j < npad; j += 128) {
 #pragma unroll
             for (int r = 0; r < TCR; ++r)
-                stg[(size_t)(r * 4 + (k & 3)) * sst + j] = (j < n) ? cur[r * npad + j] : 0.0;
+                stg[(size_t)(r * 4 + (k & 3)) * sst + j] = (j < n) ? cur[(j) * TCR + r] : 0.0;
         }
         if (k + 1 < k_end) {
             const double inv = c_inv_int[k + 1];       // 1 / (k + 1), correctly rounded (host table)
             if (j0 < n) {
                 double acc[TCR];
 #pragma unroll
-                for (int r = 0; r < TCR; ++r) acc[r] = cur[r * npad + j0] * mu;
+                for (int r = 0; r < TCR; ++r) acc[r] = cur[(j0) * TCR + r] * mu;
                 if (cnt0 == 255) {
                     for (int rr = 0; rr < n; ++rr) {
                         const double q = Q[(size_t)rr * ldq + j0];
 #pragma unroll
-                        for (int r = 0; r < TCR; ++r) acc[r] = fma(cur[r * npad + rr], q, acc[r]);
+                        for (int r = 0; r < TCR; ++r) acc[r] = fma(cur[(rr) * TCR + r], q, acc[r]);
                     }
                 } else {
 #pragma unroll
                     for (int q = 0; q < CEVB_MAX_SPARSE; ++q) {
                         if (q < cmax) {   // warp-uniform
+                            // the TCR rows of entry ridx[q] sit side by side: two 16-byte loads
+                            const double2* cp = reinterpret_cast<const double2*>(cur + ridx[q] * TCR);
 #pragma unroll
-                            for (int r = 0; r < TCR; ++r)
-                                acc[r] = fma(cur[r * npad + ridx[q]], qval[q], acc[r]);
+                            for (int r = 0; r < TCR; r += 2) {
+                                const double2 c2 = cp[r >> 1];
+                                acc[r] = fma(c2.x, qval[q], acc[r]);
+                                acc[r + 1] = fma(c2.y, qval[q], acc[r + 1]);
+                            }
                         }
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < TCR; ++r) nxt[r * npad + j0] = acc[r] * inv;
+                for (int r = 0; r < TCR; ++r) nxt[(j0) * TCR + r] = acc[r] * inv;
             }
             for (int j = tid + 128; j < n; j += 128) {   // n > 128
                 const int cnt = cnt_c[j];
                 double acc[TCR];
 #pragma unroll
-                for (int r = 0; r < TCR; ++r) acc[r] = cur[r * npad + j] * mu;
+                for (int r = 0; r < TCR; ++r) acc[r] = cur[(j) * TCR + r] * mu;
                 const int lim = (cnt == 255) ? n : cnt;
                 for (int q = 0; q < lim; ++q) {
                     const int rr = (cnt == 255) ? q : idx_c[(size_t)q * n + j];
                     const double qv = Q[(size_t)rr * ldq + j];
 #pragma unroll
-                    for (int r = 0; r < TCR; ++r) acc[r] = fma(cur[r * npad + rr], qv, acc[r]);
+                    for (int r = 0; r < TCR; ++r) acc[r] = fma(cur[(rr) * TCR + r], qv, acc[r]);
                 }
 #pragma unroll
-                for (int r = 0; r < TCR; ++r) nxt[r * npad + j] = acc[r] * inv;
+                for (int r = 0; r < TCR; ++r) nxt[(j) * TCR + r] = acc[r] * inv;
             }
         }
         __syncthreads();
@@ -2247,7 +2256,7 @@ extern "C" int cevb_taylor_prepare(const double* pw, int B, int n, double t_max,
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int npad = round_up(n, 8);
-    q_structure_kernel<<<B, 128, 0, st>>>(pw, n, ldq_of(n), norms, csc, csc_cnt);
+    q_structure_kernel<<<B, 128, 0, st>>>(pw, n, ldq_of(n), norms, csc, csc_cnt, t_max);
     CEVB_CHECK_LAUNCH("q_structure_kernel");
     static bool inv_ready = false;
     if (!inv_ready) {

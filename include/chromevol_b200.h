@@ -69,6 +69,7 @@ extern "C" {
 #define CEVB_NORM_SHIFT 11   /* mu = max(0, -min_i Q_ii): the series path sums (Q + mu I)      */
 #define CEVB_NORM_SHIFTED 12 /* nu = min(||Q + mu I||_1, ||Q + mu I||_inf)                       */
 #define CEVB_NORM_GENERATOR 13 /* 1.0 if Q is a finite generator (off-diagonals >= 0) with nu > 0 */
+#define CEVB_NORM_CHUNKS 14  /* series chunks (of 4 degrees) the longest branch t_max can need, 1..CEVB_TAYLOR_KC */
 
 /* info flags (bits 16..) */
 #define CEVB_INFO_IDENTITY_T0 1   /* t == 0 -> exact identity (AR:146-148)            */
