@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes
 import gc
+import os
 
 import numpy as np
 import torch
@@ -185,7 +186,7 @@ class LikelihoodEngine:
         # small batches (one evaluation, the 9 points of a finite-difference gradient) are launch-
         # bound: about 50 kernels of a few microseconds each.  Their launch sequence is captured
         # once per batch size into a CUDA graph and replayed.
-        self.graph_max_batch = 32
+        self.graph_max_batch = int(os.environ.get("CEVB_GRAPH_MAX", "32"))
         self._graphs = {}
         self.chunk = int(chunk)
         self.overflow_events = 0

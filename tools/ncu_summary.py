@@ -20,6 +20,11 @@ KEYS = [
     "sm__warps_active.avg.pct_of_peak_sustained_active",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum", "smsp__cycles_active.avg",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
+    "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
 ]
 
 
@@ -57,6 +62,11 @@ def raw(path, flt=None):
         for k in KEYS:
             if k in hdr:
                 print(f"   {k:80s} {r[hdr.index(k)]:>16s} {units[hdr.index(k)]}")
+        stalls = [(float(r[i] or 0), h) for i, h in enumerate(hdr)
+                  if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")]
+        top = ", ".join(f"{h.split('stalled_')[1].split('_per_issue')[0]} {v:.2f}"
+                        for v, h in sorted(stalls, reverse=True)[:6])
+        print(f"   warps stalled per issued instruction (top): {top}")
 
 
 def source(path, which="0", top="25"):
