@@ -17,9 +17,11 @@ import argparse
 import logging
 import os
 
+import numpy as np
 import pandas as pd
 
-from .ancestral_reconstruction import (calculate_model_selection_criteria,
+from .ancestral_reconstruction import (ChromEvolLikelihoodCalculator,
+                                       calculate_model_selection_criteria,
                                        perform_chromevol_analysis)
 from .newick import Tree
 
@@ -111,11 +113,39 @@ def write_ancestral_states_report(tree, output_file, use_chromevol_method=True):
     return frame
 
 
+def write_reconstructions_report(tree, counts_dict, model, root_prior_state, output_file):
+    """ADDITIVE (no reference counterpart; AR:274-295 documents the missing down-pass): the marginal
+    posterior arg max and the joint (Pupko) assignment of every node next to the reference's
+    up-pass arg max, with the parameters the analysis ended with.  The reference-shaped report
+    and the node attributes it reads are not touched."""
+    calculator = ChromEvolLikelihoodCalculator(tree, counts_dict, model)
+    root_freq = np.ones(model.max_chr + 1) / (model.max_chr + 1)
+    if root_prior_state is not None and 0 <= root_prior_state <= model.max_chr:
+        root_freq = np.zeros(model.max_chr + 1)
+        root_freq[root_prior_state] = 1.0
+    calculator.set_root_frequencies(root_freq)
+    calculator.marginal_reconstruction()
+    _, joint_logp = calculator.joint_reconstruction()
+    rows = []
+    for k, node in enumerate(tree.traverse()):
+        name = node.name if node.name else f"Internal_Node_{k}"
+        rows.append({"node_name": name,
+                     "up_pass_count": getattr(node, "ml_count", None),
+                     "marginal_count": int(node.marginal_count),
+                     "marginal_probability": float(node.marginal_probability),
+                     "joint_count": int(node.joint_count)})
+    frame = pd.DataFrame(rows)
+    frame.to_csv(output_file, index=False)
+    logging.info(f"* Marginal / joint reconstructions saved to {output_file} "
+                 f"(joint log-probability {joint_logp:.4f})")
+    return frame
+
+
 def ancestral_reconstruction(tree_file, counts_file, map_file, output_image, output_ancestral_states,
                              output_rearrangements, root_constraint_count, layout,
                              show_branch_length, show_support, analyze_pairs_list, dpi,
                              use_chromevol_method, optimize_model_params, perform_model_selection,
-                             max_chromosome_val, initial_model_params_dict):
+                             max_chromosome_val, initial_model_params_dict, output_reconstructions=None):
     """AR:970-1152 for the ChromEvol branch; returns the annotated tree (the reference returns
     None; callers that ignore the value see no difference)."""
     logging.info("--- Loading Data ---")
@@ -161,7 +191,7 @@ def ancestral_reconstruction(tree_file, counts_file, map_file, output_image, out
         results = calculate_model_selection_criteria(tree, counts_dict, max_chromosome_val,
                                                      root_constraint_count)
         logging.info(f"Model selection results: {results}")
-    _, tree = perform_chromevol_analysis(tree, counts_dict, max_chromosome_val,
+    model, tree = perform_chromevol_analysis(tree, counts_dict, max_chromosome_val,
                                          root_prior_state=root_constraint_count, use_ml=True,
                                          optimize_params=optimize_model_params,
                                          stochastic_mapping=True,
@@ -174,6 +204,8 @@ def ancestral_reconstruction(tree_file, counts_file, map_file, output_image, out
         logging.warning(f"Could not print tree ASCII representation: {exc}")
 
     write_ancestral_states_report(tree, output_ancestral_states, use_chromevol_method=True)
+    if output_reconstructions:
+        write_reconstructions_report(tree, counts_dict, model, root_constraint_count, output_reconstructions)
     if analyze_pairs_list:
         logging.warning("--analyze_pairs (synteny map analysis, AR:929-967) is outside the scope of this "
                         "package; skipping.")
@@ -219,6 +251,9 @@ def build_parser():
                    help='Optimize model parameters using maximum likelihood (requires --use_chromevol).')
     p.add_argument('--model_selection', action='store_true', default=False,
                    help='Perform model selection using AIC/BIC (requires --use_chromevol).')
+    p.add_argument('--out_reconstructions', type=str, default=None,
+                   help='(additive, not in the reference) Also run the marginal (up-pass + down-pass) and joint '
+                        '(Pupko) ancestral reconstructions with the final parameters and write them to this CSV.')
     return p
 
 
@@ -246,7 +281,8 @@ def main(argv=None):
         show_branch_length=args.show_branch_length, show_support=args.show_support,
         analyze_pairs_list=args.analyze_pairs, dpi=args.dpi, use_chromevol_method=args.use_chromevol,
         optimize_model_params=args.optimize_params, perform_model_selection=args.model_selection,
-        max_chromosome_val=args.max_chr_number, initial_model_params_dict=None)
+        max_chromosome_val=args.max_chr_number, initial_model_params_dict=None,
+        output_reconstructions=args.out_reconstructions)
     return 0 if tree is not None else 1
 
 

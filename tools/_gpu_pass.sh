@@ -1,4 +1,9 @@
 mkdir -p gpurun_out
-( timeout 1200 python -m pytest tests/test_gpu_fused.py tests/test_gpu_parity.py tests/test_gpu_ring_parts.py -x -q ) > gpurun_out/r2s_tests.log 2>&1
-timeout 200 python tools/apply_ab.py prep2 > gpurun_out/r2s_ab.log 2>&1
-grep -E "passed|failed" gpurun_out/r2s_tests.log | tail -3; cat gpurun_out/r2s_ab.log | cut -c1-400
+timeout 600 python bench.py --skip-cpu --no-configs > gpurun_out/r2v_bench_g32.json 2> gpurun_out/r2v_bench_g32.err
+CEVB_GRAPH_MAX=512 timeout 600 python bench.py --skip-cpu --no-configs > gpurun_out/r2v_bench_g512.json 2> gpurun_out/r2v_bench_g512.err
+python - <<'P'
+import json
+for t in ("g32","g512"):
+    d=json.loads([l for l in open(f"gpurun_out/r2v_bench_{t}.json") if l.startswith("{")][-1])
+    print(t, d["value"], d["e2e"], d["single_vector"])
+P
