@@ -311,7 +311,14 @@ def run_ours(args):
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    t_res = D.max_across_ranks(ev0.elapsed_time(ev1) * 1e-3, dev)
+    t_own = ev0.elapsed_time(ev1) * 1e-3
+    t_res = D.max_across_ranks(t_own, dev)
+    # every rank's own device time: the ranks evaluate different random batches (different series
+    # lengths), so part of the gap to perfect weak scaling is the slowest batch, not communication
+    per_rank_ms = [t_own / args.steps * 1e3]
+    if world > 1:
+        own = torch.tensor([t_own / args.steps * 1e3], dtype=torch.float64, device=dev)
+        per_rank_ms = D.all_gather_ragged(own, world, world).cpu().tolist()
     n_chunks = eng.n_chunks
     launches_per_step = n_chunks * eng.launches_per_chunk()      # of our kernels, all stream slices
     # Pade orders / squaring counts the device chose, from one extra untimed step (deterministic)
@@ -493,6 +500,7 @@ def run_ours(args):
                           "ms": t_single * 1e3, "evals_per_s": 1.0 / t_single},
         "repivot_events": eng.repivot_events,
         "clocks": clocks,
+        "per_rank_ms_per_step": per_rank_ms,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
@@ -667,8 +675,14 @@ def run_other_configs(dev, rank, world, eng2, tree2, counts2):
     reps = 1_000_000
     lo, hi = D.shard_bounds(reps, rank, world)
     row = synthetic.default_param_row()
-    mapper.simulate(flat, row, MAX_CHR + 1, root, reps, 7, rep_begin=lo, rep_end=min(hi, lo + 4096),
-                    return_device=True)
+    warm = mapper.simulate(flat, row, MAX_CHR + 1, root, reps, 7, rep_begin=lo, rep_end=min(hi, lo + 4096),
+                           return_device=True)
+    if world > 1:
+        # the first all-reduce of this size sets up NCCL's channels (90 ms at N=8): untimed, like
+        # the warm-up steps of the main loop
+        D.sum_across_ranks(warm[0])
+        D.sum_across_ranks(warm[2].to(torch.float64))
+    del warm
     sync()
     e0.record()
     hist, sums, n_events = mapper.simulate(flat, row, MAX_CHR + 1, root, reps, 7, rep_begin=lo, rep_end=hi,

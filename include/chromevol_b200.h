@@ -124,10 +124,14 @@ int cevb_expm_branches_list(const double* pw, const double* norms, const uint16_
  * with C_k formed once per vector.  cevb_taylor_prepare needs only slot 0 of pw (Q); t_max > 0
  * promises that no branch is longer than t_max, so only the chunks such a branch can need are
  * formed (<= 0: all of them).  It writes
- *   norms[b][CEVB_NORM_ONE / _SHIFT / _SHIFTED] = ||Q_b||_1, mu_b, nu_b,
+ *   norms[b][CEVB_NORM_ONE / _SHIFT / _SHIFTED / _GENERATOR / _CHUNKS] = ||Q_b||_1, mu_b, nu_b,
+ *   "Q_b is a finite generator", chunks the longest branch needs,
  *   the compressed-column structure csc / csc_cnt and
- *   tc [B][n][CEVB_TAYLOR_KC][n_pad][4]   (n_pad = n rounded up to 8; cevb_taylor_doubles(n)
- *   doubles per vector); chunk c of row i holds degrees 4c..4c+3 interleaved per column.
+ *   tc: cevb_taylor_doubles(n) doubles per vector -- an opaque table for the other cevb_taylor_*
+ *   calls: per (row, pass of 13 column tiles) CEVB_TAYLOR_KC chunks of [13 slots][8 columns]
+ *   [4 degrees] (chunk c = degrees 4c..4c+3, tiles in the order in which they first hold a
+ *   non-zero, only that slot prefix is written), four 64-bit meta words per (row, pass), and for
+ *   generator vectors with n <= 104 a scaled TF32 copy for the observed-leaf launch.
  * The number of terms for a pair is the smallest K + 1 with
  *     x^(K+1)/(K+1)! / (1 - x/(K+2)) e^{-mu t} <= CEVB_TAYLOR_TRUNC,  x = nu t;
  * cevb_expm_plan lists every (vector, branch length) pair for which 4 * CEVB_TAYLOR_KC = 64 terms do not
