@@ -93,6 +93,42 @@ def test_count_distribution_against_oracle_simulator():
     assert (res.sums[:, :, 0].sum(axis=0) > 0).all()
 
 
+def test_config5_workload_against_oracle_simulator():
+    """BASELINE configs[4]'s own workload (1,000 taxa, N=100, default rates, root state 20):
+    per-branch mean event counts of 200k device replicates against 2,000 replicates of the oracle
+    simulator (AR:467-576 restated; pinned to the live reference), z-test per (branch, type) on
+    the branches where events are frequent enough, and the per-replicate totals per type."""
+    from chromevol_enhanced_b200 import synthetic
+    tree = synthetic.random_tree(1000, seed=1)
+    params = O.default_params()
+    root_probs = np.zeros(101)
+    root_probs[20] = 1.0
+    R, Rc = 200_000, 2000
+    flat, res = _run(tree, params, 100, root_probs, R, seed=21)
+    assert not res.overflowed()
+    order, out = O.stochastic_mapping_counts(tree, O.build_q(params, 100), root_probs, Rc,
+                                             np.random.default_rng(8))
+    idx = np.array([flat.index[id(nd)] for nd in order])
+    mean_gpu = res.sums[idx, :, 0] / R                              # (branches, 8)
+    mean_cpu = out.mean(axis=0)
+    var_cpu = out.var(axis=0)
+    se = np.sqrt(var_cpu / Rc + var_cpu / R)
+    busy = mean_cpu * Rc >= 30                                      # enough events to test the mean
+    assert busy.sum() > 300
+    z = np.abs(mean_gpu - mean_cpu)[busy] / se[busy]
+    assert z.max() < 5.5, z.max()                                    # ~1,000 tests: 5.5 sigma ~ 4e-5 overall
+    assert abs(z.mean() - np.sqrt(2 / np.pi)) < 0.2                  # |N(0,1)| on average: no systematic bias
+    # totals per replicate and type
+    tot_gpu = res.sums[:, :, 0].sum(axis=0) / R
+    tot_cpu = out.sum(axis=1)                                       # (Rc, 8)
+    for e in range(8):
+        if tot_cpu[:, e].mean() > 0.05:
+            se_t = tot_cpu[:, e].std() / np.sqrt(Rc)
+            assert abs(tot_gpu[e] - tot_cpu[:, e].mean()) < 5.0 * se_t, e
+    # no base number: the two base-number event types never occur
+    assert res.sums[:, 3:5, 0].sum() == 0
+
+
 def test_sharding_invariance_and_seed_dependence(shipped, golden):
     arrays, _ = golden
     newick, _ = shipped

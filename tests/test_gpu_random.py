@@ -83,3 +83,37 @@ def test_random_problem_matches_oracle(seed):
             v = vectors[id(flat.nodes[k])]
             p = v / v.sum() if v.sum() > 0 else np.full(N + 1, 1.0 / (N + 1))
             assert abs(p[got[k]] - p[want[k]]) <= 1e-9 * max(p.max(), 1e-300), (seed, int(k))
+
+
+@pytest.mark.parametrize("scale", [1e-3, 3e-2, 1.0])
+def test_floor_driven_likelihoods_through_the_tf32_leaf_launch(scale):
+    """Improbable data: tip counts scattered over 1..100 under slow rates, so most of every leaf
+    branch's transition column sits on the 1e-12 floor and the row-sum correction of the leaf
+    launch (TF32 tensor cores for generator vectors) matters as much as it ever
+    can.  logL and the per-leaf-branch messages against the oracle; the FP64 leaf kernel
+    (CEVB_LOWP is a library-wide knob, so: a vector whose Q is no generator) gives the same."""
+    from chromevol_enhanced_b200 import synthetic
+    from chromevol_enhanced_b200.engine import LikelihoodEngine
+    from chromevol_enhanced_b200.flatten import FlatTree
+    rng = np.random.default_rng(5)
+    N = 100
+    tree = synthetic.random_tree(150, seed=41, mean_len=0.05)
+    counts = {leaf.name: int(rng.integers(1, N + 1)) for leaf in tree.get_leaves()}
+    rows = synthetic.random_param_rows(6, seed=43, linear='positive')
+    rows[:, :7] *= scale
+    rows[5, 7] = -1e-4                      # tiny negative linear rate: FP64 leaf kernel, same physics
+    flat = FlatTree(tree, counts, N)
+    eng = LikelihoodEngine(flat)
+    ll = eng.log_likelihood(rows).cpu().numpy()
+    for b in range(rows.shape[0]):
+        ref, vectors, resc = O.log_likelihood(tree, counts, N, synthetic.row_to_dict(rows[b]))
+        assert np.isfinite(ref)
+        assert ll[b] == pytest.approx(ref, rel=1e-9), (scale, b, ll[b], ref)
+        assert int(eng.rescale_counts[b]) == resc
+    # node vectors of one generator vector, entry by entry relative to each vector's largest entry
+    eng.log_likelihood(rows[2:3])
+    got = eng.node_vectors(0).cpu().numpy()
+    _, vectors, _ = O.log_likelihood(tree, counts, N, synthetic.row_to_dict(rows[2]))
+    for k, nd in enumerate(flat.nodes):
+        v = vectors[id(nd)]
+        assert np.abs(got[k] - v).max() <= 1e-9 * v.max(), (scale, k)
