@@ -1815,7 +1815,7 @@ static int fused_query() {
 //   CEVB_TW / CEVB_TM / CEVB_TS   branch-count thresholds of the CTA shapes (launch_apply_shapes)
 //   CEVB_DENSE=1                  coefficient table without the sparse slot order (A/B runs)
 struct Tuning {
-    int tw, tm, ts, td, dense, skew, ring_small, ring_medium, ring_wide, ring_lowp, lowp;
+    int tw, tm, ts, td, dense, skew, ring_small, ring_medium, ring_wide, ring_lowp, lowp, eval_ry;
 };
 static const Tuning& tuning() {
     static const Tuning t = [] {
@@ -1836,6 +1836,7 @@ static const Tuning& tuning() {
         x.ring_lowp = env("CEVB_RING_L", LP_MAXSTAGE * L_KB);  // k-block slots of leaf_lowp_kernel
         // (small values force the multi-part streaming of an item: tests/test_gpu_ring_parts.py)
         x.lowp = env("CEVB_LOWP", 1);            // TF32 floor correction for the leaf launch
+        x.eval_ry = env("CEVB_EVAL_RY", 2);      // row split of the squaring path's series launch (0.69 -> 0.47 ms per 512 vectors)
         return x;
     }();
     return t;
@@ -1853,6 +1854,10 @@ static int launch_apply_one(ApplyArgs& a, int B, cudaStream_t st) {
         const int ry_max = (a.n + 7) / 8;
         if (ry > ry_max) ry = ry_max;
     }
+    // The series launch of the squaring path: a handful of CTAs (the longest branches of the few
+    // vectors that need squarings) do all the work, 64 terms on every row, while the rest of the
+    // grid leaves at once -- its duration is the life of ONE working CTA, so the rows are split
+    if (MODE == APPLY_EVAL && ry < tuning().eval_ry) ry = tuning().eval_ry;
     a.rows_per_cta = (a.n + ry - 1) / ry;
     ry = (a.n + a.rows_per_cta - 1) / a.rows_per_cta;
     a.meta_bytes = (int)apply_meta_bytes(a.rows_per_cta * a.npass);
