@@ -419,7 +419,7 @@ def run_ours(args):
     peak_src = "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)"
     apply_tf = work["algorithmic_flops"] / apply_s / 1e12 if apply_s > 0 else None
     apply_exec_tf = work["dmma_flops"] / apply_s / 1e12 if apply_s > 0 else None
-    # pairs with t||Q||_1 > 5.4: series at t 2^-s (2 n^2 per term) + s squarings (2 n^3 each)
+    # pairs with nu t > 15.6: series at t 2^-s (2 n^2 per term) + s squarings (2 n^3 each)
     list_pairs = int(s_list.size)
     list_flops = float(np.sum(2.0 * n ** 3 * s_list)) + 2.0 * n * n * 4 * accounting.KC * list_pairs
     list_tf = list_flops / expm_s / 1e12 if (expm_s > 0 and list_pairs) else None
@@ -488,7 +488,7 @@ def run_ours(args):
                               "achieved": list_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                               "frac": (list_tf / fp64_peak) if list_tf else None,
                               "pairs": list_pairs, "squarings_hist": s_hist,
-                              "note": "pairs whose series needs more than 48 terms; algorithmic = 96 n^2 (series) + 2 s n^3 (squarings)"},
+                              "note": "pairs whose series needs more than 64 terms; algorithmic = 128 n^2 (series) + 2 s n^3 (squarings)"},
         "roofline_combine": {"kernel": "combine_level_kernel", "bound": "hbm", "achieved": combine_gbs,
                              "peak": hbm_peak, "unit": "GB/s",
                              "frac": (combine_gbs / hbm_peak) if combine_gbs else None,

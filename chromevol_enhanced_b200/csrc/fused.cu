@@ -7,21 +7,26 @@
 // followed, per parent node, by the product over children in file order with the reference's
 // conditional rescale (AR:238-243) and the root log-likelihood (AR:251-272).
 //
-// Every branch of one parameter vector shares Q (the CLI never sets branch_params), so
-//     expm(Q t) = sum_k t^k C_k,   C_k = Q^k / k!,
+// Every branch of one parameter vector shares Q (the CLI never sets branch_params), so with the
+// uniformisation shift mu = max(0, -min_i Q_ii)
+//     expm(Q t) = e^{-mu t} sum_k t^k C_k,   C_k = (Q + mu I)^k / k!,
 // is a polynomial in the SCALAR t with matrix coefficients that are formed once per vector
-// (taylor_coeff_kernel; Q has <= 9 non-zeros per column, so each C_k costs O(9 n^2)).  For
-// eta = t ||Q||_1 <= 5.4 (the same bound scipy's Pade-13 uses unscaled) the series is summed
-// directly: evaluating it for many branches at once is the dense contraction
-//     P[e, (i,j)] = sum_k T[e,k] C[k,(i,j)],   T[e,k] = t_e^k,
+// (taylor_coeff_kernel; Q has <= 9 non-zeros per column, so each C_k costs O(9 n^2)) and, for a
+// generator, without cancellation.  Evaluating it for many branches at once is the dense
+// contraction
+//     P[e, (i,j)] = sum_k T[e,k] C[k,(i,j)],   T[e,k] = e^{-mu t_e} t_e^k,
 // which taylor_apply_kernel runs on the FP64 tensor cores (DMMA.8x8x4: M = 8 branches, N = 8
 // columns j of one row i, K = 4 series terms) with the coefficient rows staged in shared memory
-// by bulk async copies (cp.async.bulk + mbarrier, double buffered).  The floor, the row sum and
-// the dot product with L_child are applied to the accumulator fragments in registers, so only
-// w (n doubles per branch) leaves the SM.  The number of terms is chosen per branch from eta so
-// that the truncation bound eta^(K+1)/(K+1)! / (1 - eta/(K+2)) is below 1e-18.
-// Branches with eta > 5.4 need squarings and therefore a materialised matrix: they are routed
-// (cevb_expm_plan) to the Pade kernel of expm.cu, whose P the combine kernel reads.
+// by bulk async copies (cp.async.bulk + mbarrier ring).  The floor, the row sum and the dot
+// product with L_child are applied to the accumulator fragments in registers, so only w (n
+// doubles per branch) leaves the SM.  Branches that end in an observed leaf need one column of
+// P and, for the row sum, only the floor correction of the rest: leaf_lowp_kernel (FP64 column +
+// TF32 tensor cores).  The number of terms is chosen per (vector, branch) from x = nu t,
+// nu = min(||Q + mu I||_1, ||Q + mu I||_inf), so that the truncation bound
+// x^(K+1)/(K+1)! / (1 - x/(K+2)) e^{-mu t} is below 1e-18.  Pairs that would need more than the 64
+// tabulated terms (x above about 15.6) are scaled and squared and therefore materialised: the
+// series at t 2^-s by the same kernel (MODE 2), the squarings by square_post_kernel, and the
+// combine kernel streams their P.
 #include <stdlib.h>
 
 #include <type_traits>
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
     const int kc_need = (int)norms[(size_t)b * CEVB_NNORM + CEVB_NORM_CHUNKS];
     const int k_end = 4 * kc_need;
     // The sparse column of (Q + mu I) a thread multiplies with is the same for every row and
-    // all 39 steps: it is kept in registers (<= 12 entries), so a step is shared-memory loads
+    // all steps: it is kept in registers (<= 12 entries), so a step is shared-memory loads
     // and FMAs only, for TCR rows at once.  Columns beyond 128 (n > 128) and columns with more
     // than 12 non-zeros re-read the structure from global memory.
     const int j0 = tid;

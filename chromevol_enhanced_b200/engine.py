@@ -5,9 +5,10 @@ This is the additive, batched entry point that sits beside the reference-shaped 
 memory and streams only); all arithmetic happens in the hand-written kernels behind the C ABI.
 
 Pipeline per chunk of parameter vectors (one stream, no host synchronisation inside):
-  path="fused" (default): P(t) is never written to HBM for branches with t ||Q||_1 <= 5.4
-    cevb_build_q -> cevb_expm_prepare -> cevb_taylor_prepare -> cevb_expm_plan ->
-    cevb_expm_branches_list (only the pairs that need squarings) -> cevb_prune_fused
+  path="fused" (default): P(t) is never written to HBM for pairs whose series converges within
+  64 terms (nu t below about 15.6; the rest is scaled and squared into a few P slots)
+    cevb_build_q -> cevb_taylor_prepare -> cevb_expm_plan ->
+    cevb_taylor_matrices (only the pairs that need squarings) -> cevb_prune_fused
   path="materialised": every P(t) by Pade + scaling-and-squaring, then streamed by the pruning
     cevb_build_q -> cevb_expm_prepare -> cevb_expm_branches -> cevb_prune
 [-> cevb_argmax_states]
@@ -125,7 +126,7 @@ class LikelihoodEngine:
 
     def __init__(self, flat: FlatTree, device=None, max_workspace_bytes=32 << 30, chunk=None,
                  path="fused", squaring="series", n_streams=4):
-        """path: "fused" (series on the tensor cores, P never written for t||Q||_1 <= 5.4) or
+        """path: "fused" (series on the tensor cores, P never written for nu t <= 15.6) or
         "materialised" (every P by the Pade kernel).  squaring: how the fused path forms the
         matrices that need scaling and squaring -- "series" (series at t 2^-s + squarings in
         shared memory) or "pade" (the scipy-algorithm kernel on a work list)."""
@@ -165,7 +166,7 @@ class LikelihoodEngine:
         mat_bytes = 8 * self.n * self.ldp
         if path == "fused":
             # per vector: powers + series coefficients + node vectors + w; the rest of the budget
-            # holds materialised matrices (only pairs with t ||Q||_1 > 5.4 need one)
+            # holds materialised matrices (only pairs with nu t > 15.6 need one)
             per_vec = (8 * 7 * self.n * self.lib.cevb_ldq(self.n)
                        + 8 * self.lib.cevb_taylor_doubles(self.n)
                        + 24 * flat.n_nodes * self.ldp + 16 * flat.n_t + 64 * self.n)
