@@ -1,6 +1,6 @@
 """Table of every taylor_apply_kernel launch of one step from an `ncu --set full` raw CSV
-(`ncu -i rep --page raw --csv > raw.csv`) and the mean DRAM bytes per launch for
-profiles/traffic.json.
+(`ncu -i rep --page raw --csv > raw.csv`); optionally also the mean DRAM bytes per launch as a
+small JSON (bench.py itself reads profiles/r02_apply_traffic.csv.gz, see tools/_evidence.sh).
 usage: python tools/apply_levels_table.py raw.csv out.txt [traffic.json]"""
 import csv
 import json
