@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -65,12 +65,19 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        """Host time at which the timed region starts (the sampler itself is started before the
+        warm-up steps: nvidia-smi needs ~0.1 s to deliver its first line and the timed region of
+        five 16 ms steps is shorter than that)."""
+        self.t_begin = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t_end = time.perf_counter()
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -78,7 +85,12 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        t_begin = getattr(self, "t_begin", 0.0)
+        inside = [ln for (ts, ln) in self.lines if t_begin <= ts <= t_end + 0.03]
+        # a line reports the state a few ms before it arrives; if the region was too short for any
+        # line to land inside it, the lines of the warm-up steps right before it (same load) stand in
+        chosen = inside if inside else [ln for (ts, ln) in self.lines if ts >= t_begin - 0.25]
+        for line in chosen:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:
                 continue
@@ -94,7 +106,8 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(smax)) if smax else None,
                 "power_w_max": float(max(power)) if power else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_inside_timed_region": len(inside) if sm else 0,
+                "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------
@@ -296,14 +309,16 @@ def run_ours(args):
         return out
 
     # ---- device-resident timing ("value")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # before the warm-up steps, see ClockSampler.begin
     for _ in range(args.warmup):
         step_resident()
     drain()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if rank == 0:
+        sampler.begin()
     ev0.record()
     for _ in range(args.steps):
         step_resident()

@@ -14,7 +14,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'taylor_apply|leaf_lowp' --launch-skip 22 --launch-count 22 \
     -o /tmp/${T}_apply -f python tools/step_once.py > gpurun_out/${T}_ncu_apply.log 2>&1
 ncu -i /tmp/${T}_apply.ncu-rep --page raw --csv > gpurun_out/${T}_raw.csv 2>/dev/null
-timeout 900 ncu --set full --clock-control none -k regex:'taylor_coeff|square_post|combine_level_warp' --launch-skip 3 --launch-count 3 \
+timeout 900 ncu --set full --clock-control none -k regex:'taylor_coeff|square_post|q_structure|expm_plan|build_q' --launch-skip 5 --launch-count 5 \
     -o /tmp/${T}_other -f python tools/step_once.py > gpurun_out/${T}_ncu_other.log 2>&1
 timeout 300 python tools/mapper_once.py > gpurun_out/${T}_mapper_plain.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none -k regex:stoch_map --launch-skip 1 --launch-count 1 \
