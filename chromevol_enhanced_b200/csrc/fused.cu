@@ -246,8 +246,8 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
                                                            int dense, int lowp_on,
                                                            double* __restrict__ tc) {
     extern __shared__ double shc[];
-    double* cur = shc;                    // [npad][TCR]: the TCR rows of one column side by side
-    double* nxt = shc + TCR * npad;       // [npad][TCR]
+    double* cur = shc;                    // [TCR][npad] (row-major per row: the gather of a step reads
+    double* nxt = shc + TCR * npad;       // neighbouring columns, i.e. conflict-free 8-byte loads)
     // staging of one chunk, DEGREE-major: [TCR][4 degrees][sst] with a row stride of npad + 4
     // doubles, so that the per-degree store of a step (lane = column) and the TF32 read-out are
     // conflict-free and the two degree rows a write-out lane pairs up sit 8 banks apart (the
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
     }
     for (int j = tid; j < npad; j += 128) {
 #pragma unroll
-        for (int r = 0; r < TCR; ++r) cur[(j) * TCR + r] = (j == i0 + r) ? 1.0 : 0.0;
+        for (int r = 0; r < TCR; ++r) cur[r * npad + j] = (j == i0 + r) ? 1.0 : 0.0;
     }
     if (tid < TCR * TC_MAXPASS) {
         const int r = tid / TC_MAXPASS, p = tid - r * TC_MAXPASS;
@@ -326,52 +326,47 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
         for (int j = tid; j < npad; j += 128) {
 #pragma unroll
             for (int r = 0; r < TCR; ++r)
-                stg[(size_t)(r * 4 + (k & 3)) * sst + j] = (j < n) ? cur[(j) * TCR + r] : 0.0;
+                stg[(size_t)(r * 4 + (k & 3)) * sst + j] = (j < n) ? cur[r * npad + j] : 0.0;
         }
         if (k + 1 < k_end) {
             const double inv = c_inv_int[k + 1];       // 1 / (k + 1), correctly rounded (host table)
             if (j0 < n) {
                 double acc[TCR];
 #pragma unroll
-                for (int r = 0; r < TCR; ++r) acc[r] = cur[(j0) * TCR + r] * mu;
+                for (int r = 0; r < TCR; ++r) acc[r] = cur[r * npad + j0] * mu;
                 if (cnt0 == 255) {
                     for (int rr = 0; rr < n; ++rr) {
                         const double q = Q[(size_t)rr * ldq + j0];
 #pragma unroll
-                        for (int r = 0; r < TCR; ++r) acc[r] = fma(cur[(rr) * TCR + r], q, acc[r]);
+                        for (int r = 0; r < TCR; ++r) acc[r] = fma(cur[r * npad + rr], q, acc[r]);
                     }
                 } else {
 #pragma unroll
                     for (int q = 0; q < CEVB_MAX_SPARSE; ++q) {
                         if (q < cmax) {   // warp-uniform
-                            // the TCR rows of entry ridx[q] sit side by side: two 16-byte loads
-                            const double2* cp = reinterpret_cast<const double2*>(cur + ridx[q] * TCR);
 #pragma unroll
-                            for (int r = 0; r < TCR; r += 2) {
-                                const double2 c2 = cp[r >> 1];
-                                acc[r] = fma(c2.x, qval[q], acc[r]);
-                                acc[r + 1] = fma(c2.y, qval[q], acc[r + 1]);
-                            }
+                            for (int r = 0; r < TCR; ++r)
+                                acc[r] = fma(cur[r * npad + ridx[q]], qval[q], acc[r]);
                         }
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < TCR; ++r) nxt[(j0) * TCR + r] = acc[r] * inv;
+                for (int r = 0; r < TCR; ++r) nxt[r * npad + j0] = acc[r] * inv;
             }
             for (int j = tid + 128; j < n; j += 128) {   // n > 128
                 const int cnt = cnt_c[j];
                 double acc[TCR];
 #pragma unroll
-                for (int r = 0; r < TCR; ++r) acc[r] = cur[(j) * TCR + r] * mu;
+                for (int r = 0; r < TCR; ++r) acc[r] = cur[r * npad + j] * mu;
                 const int lim = (cnt == 255) ? n : cnt;
                 for (int q = 0; q < lim; ++q) {
                     const int rr = (cnt == 255) ? q : idx_c[(size_t)q * n + j];
                     const double qv = Q[(size_t)rr * ldq + j];
 #pragma unroll
-                    for (int r = 0; r < TCR; ++r) acc[r] = fma(cur[(rr) * TCR + r], qv, acc[r]);
+                    for (int r = 0; r < TCR; ++r) acc[r] = fma(cur[r * npad + rr], qv, acc[r]);
                 }
 #pragma unroll
-                for (int r = 0; r < TCR; ++r) nxt[(j) * TCR + r] = acc[r] * inv;
+                for (int r = 0; r < TCR; ++r) nxt[r * npad + j] = acc[r] * inv;
             }
         }
         __syncthreads();
