@@ -35,7 +35,9 @@
 
 // Timing experiments only (tools/stub_build.py): -DCEVB_STUB=<mask> removes parts of the apply
 // kernel -- 1 epilogue arithmetic, 2 ring waits and copies, 4 the DMMAs of chunks >= 1, 8 the
-// per-row reduction and stores.  Results are wrong with any bit set; the product build has 0.
+// per-row reduction and stores -- and of the coefficient kernel -- 16 the TF32 copy, 32 the
+// activity scan / slot bookkeeping / write-out of a chunk, 64 the sparse product of a step.
+// Results are wrong with any bit set; the product build has 0.
 #ifndef CEVB_STUB
 #define CEVB_STUB 0
 #endif
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
     // 67 % LSU utilisation per 512-vector launch in the round-2 ncu capture)
     double* stg = shc + 2 * TCR * npad;
     const int sst = npad + 4;
-    __shared__ uint8_t s_act[TCR][TC_MAXPASS * F_JT];     // tile holds a non-zero in this chunk
+    uint32_t* tfs = reinterpret_cast<uint32_t*>(stg + 4 * TCR * sst);   // [TCR][4][104] parked TF32 words
     __shared__ uint8_t s_perm[TCR][TC_MAXPASS][16];       // slot -> tile of the pass
     __shared__ int8_t s_slot[TCR][TC_MAXPASS][16];        // tile of the pass -> slot (-1: none yet)
     __shared__ int s_nslot[TCR][TC_MAXPASS];
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
 #pragma unroll
                         for (int r = 0; r < TCR; ++r) acc[r] = fma(cur[r * npad + rr], q, acc[r]);
                     }
-                } else {
+                } else if (!(CEVB_STUB & 64)) {
 #pragma unroll
                     for (int q = 0; q < CEVB_MAX_SPARSE; ++q) {
                         if (q < cmax) {   // warp-uniform
@@ -372,53 +374,85 @@ __global__ void __launch_bounds__(128) taylor_coeff_kernel(const double* __restr
         __syncthreads();
         if ((k & 3) == 3) {
             const int c = k >> 2;
-            if (lowp && tid < F_JT * 8) {
-                // scaled TF32 copy of this chunk in mma.m16n8k8 B-fragment order (and zeros for
-                // the other half of the k-block if the table ends with this chunk)
+            if (!(CEVB_STUB & 16) && lowp && tid < F_JT * 8) {
+                // scaled TF32 copy in mma.m16n8k8 B-fragment order: lane 4 g + d of a tile holds
+                // degrees d (even chunk of the k-block) and d + 4 (odd chunk) of column g, so a
+                // thread's four lanes are 32 contiguous bytes.  The even chunk is parked in shared
+                // memory and the pair goes out as two 16-byte stores with the odd chunk (or at
+                // once, with zeros for the other half, if the table ends with the even chunk):
+                // full sectors instead of sixteen scattered 4-byte stores per row and chunk.
                 const int tile = tid >> 3, g8 = tid & 7, kb = c >> 1, half = c & 1;
                 const bool tail = (c == kc_need - 1) && half == 0;
                 for (int r = 0; r < TCR; ++r) {
                     if (i0 + r >= n) break;
-                    float* dst = tfb + (((size_t)(i0 + r) * L_KB + kb) * F_JT + tile) * L_TILE;
+                    uint32_t u[4];
 #pragma unroll
                     for (int d = 0; d < 4; ++d) {
                         // all 13 tiles are written: columns beyond npad are zeros
                         const float v = tid < npad ? (float)(stg[(size_t)(r * 4 + d) * sst + tid] * sc4[d]) : 0.0f;
-                        uint32_t u;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-                        dst[(g8 * 4 + d) * 2 + half] = __uint_as_float(u);
-                        if (tail) dst[(g8 * 4 + d) * 2 + 1] = 0.0f;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u[d]) : "f"(v));
+                    }
+                    uint32_t* park = tfs + (size_t)(r * 4) * (F_JT * 8) + tid;
+                    if (half == 0 && !tail) {
+#pragma unroll
+                        for (int d = 0; d < 4; ++d) park[d * (F_JT * 8)] = u[d];
+                    } else {
+                        uint32_t e[4] = {0u, 0u, 0u, 0u};     // the even chunk's words (zeros: none)
+                        if (half == 1) {
+#pragma unroll
+                            for (int d = 0; d < 4; ++d) e[d] = park[d * (F_JT * 8)];
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(
+                            tfb + (((size_t)(i0 + r) * L_KB + kb) * F_JT + tile) * L_TILE + g8 * 8);
+                        if (half == 1) {
+                            dst[0] = make_uint4(e[0], u[0], e[1], u[1]);
+                            dst[1] = make_uint4(e[2], u[2], e[3], u[3]);
+                        } else {                              // tail: this (even) chunk + zeros
+                            dst[0] = make_uint4(u[0], 0u, u[1], 0u);
+                            dst[1] = make_uint4(u[2], 0u, u[3], 0u);
+                        }
                     }
                 }
             }
-            // which tiles of this chunk hold a non-zero (a tile is 32 contiguous doubles of stg;
-            // NaN counts as non-zero)
-            for (int x = warp; x < TCR * nj; x += 4) {
-                const int r = x / nj, jt = x - r * nj;
-                const double v = stg[(size_t)(r * 4 + (lane >> 3)) * sst + jt * 8 + (lane & 7)];
-                const int any = __any_sync(0xffffffffu, !(v == 0.0));
-                if (lane == 0) s_act[r][jt] = (uint8_t)any;
+            if (CEVB_STUB & 32) {
+                double* sw2 = cur;
+                cur = nxt;
+                nxt = sw2;
+                continue;
             }
-            __syncthreads();
-            // newly active tiles take the next slots of their item
-            if (tid < TCR * npass) {
-                const int r = tid / npass, p = tid - r * npass;
-                int ns = s_nslot[r][p];
-                for (int tl = 0; tl < F_JT; ++tl) {
-                    const int jt = p * F_JT + tl;
-                    if (jt < nj && s_slot[r][p][tl] < 0 && (dense || s_act[r][jt])) {
-                        s_slot[r][p][tl] = (int8_t)ns;
-                        s_perm[r][p][ns] = (uint8_t)tl;
-                        ++ns;
+            // Warp r takes row r: which tiles of this chunk hold a non-zero (NaN counts as
+            // non-zero), then the newly active tiles take the next slots of their item -- in tile
+            // order, by a ballot instead of a serial loop -- and the chunk's slot count is noted.
+            static_assert(TCR == 4, "one warp of the 128-thread CTA per row");
+            {
+                const int r = warp;
+                unsigned long long actmask = 0ull;              // bit jt: tile jt of row r is active
+                for (int jt = 0; jt < nj; ++jt) {
+                    const double v = stg[(size_t)(r * 4 + (lane >> 3)) * sst + jt * 8 + (lane & 7)];
+                    if (__any_sync(0xffffffffu, !(v == 0.0))) actmask |= 1ull << jt;
+                }
+                for (int p = 0; p < npass; ++p) {
+                    int ns = s_nslot[r][p];
+                    const int jt = p * F_JT + lane;
+                    const bool take = lane < F_JT && jt < nj && s_slot[r][p][lane] < 0 &&
+                                      (dense || ((actmask >> jt) & 1ull));
+                    const unsigned mask = __ballot_sync(0xffffffffu, take);
+                    if (take) {
+                        const int sl = ns + __popc(mask & ((1u << lane) - 1u));
+                        s_slot[r][p][lane] = (int8_t)sl;
+                        s_perm[r][p][sl] = (uint8_t)lane;
+                    }
+                    ns += __popc(mask);
+                    if (lane == 0) {
+                        s_nslot[r][p] = ns;
+                        // chunk 0 is multiplied by straight-line code for 0, 3, 6, 9 or 13 slots
+                        // (the apply kernel interleaves it with an epilogue): its count is rounded
+                        // up; the extra slots hold zeros
+                        int cnt = ns;
+                        if (c == 0 && ns > 0) cnt = ns <= 3 ? 3 : (ns <= 6 ? 6 : (ns <= 9 ? 9 : F_JT));
+                        s_counts[r][p] |= (unsigned long long)cnt << (4 * c);
                     }
                 }
-                s_nslot[r][p] = ns;
-                // chunk 0 is multiplied by straight-line code for 0, 3, 6, 9 or 13 slots (the
-                // apply kernel interleaves it with an epilogue): its count is rounded up; the
-                // extra slots hold zeros
-                int cnt = ns;
-                if (c == 0 && ns > 0) cnt = ns <= 3 ? 3 : (ns <= 6 ? 6 : (ns <= 9 ? 9 : F_JT));
-                s_counts[r][p] |= (unsigned long long)cnt << (4 * c);
             }
             __syncthreads();
             // write-out in slot order.  Only the slot prefix the kernels copy is written: the
@@ -2272,7 +2306,8 @@ extern "C" int cevb_taylor_prepare(const double* pw, int B, int n, double t_max,
         inv_ready = true;
     }
     dim3 grid((n + TCR - 1) / TCR, B);
-    const size_t csm = sizeof(double) * (2 * TCR * (size_t)npad + 4 * TCR * (size_t)(npad + 4));
+    const size_t csm = sizeof(double) * (2 * TCR * (size_t)npad + 4 * TCR * (size_t)(npad + 4)) +
+                       sizeof(uint32_t) * 4 * TCR * (size_t)(F_JT * 8);
     static size_t coeff_attr = 0;
     if (csm > coeff_attr) {
         CEVB_CHECK_CUDA(cudaFuncSetAttribute(taylor_coeff_kernel,
