@@ -101,6 +101,14 @@ def test_flat_tree_invariants(seed, n_leaves):
         # never after its parent is combined
         assert all(f.height[c] == lv and level_of[int(f.parent[c])] >= lv for c in part)
         assert all(f.dist_eff[a] >= f.dist_eff[b] for a, b in zip(part, part[1:]))
+    # depths below the root: level-order ids make every depth a contiguous id range (the marginal
+    # down-pass and the joint backtrack launch one step per depth)
+    assert f.depth[0] == 0 and f.depth_off[0] == 0 and f.depth_off[-1] == f.n_nodes
+    assert f.n_depths == int(f.depth.max()) + 1 == len(f.depth_off) - 1
+    for k in range(1, f.n_nodes):
+        assert f.depth[k] == f.depth[f.parent[k]] + 1
+    for d in range(f.n_depths):
+        assert (f.depth[f.depth_off[d]:f.depth_off[d + 1]] == d).all()
     # pre-order for the simulator: parents before children, root first
     pos = {int(v): i for i, v in enumerate(f.preorder.tolist())}
     assert f.preorder[0] == 0 and sorted(pos) == list(range(f.n_nodes))
