@@ -14,7 +14,7 @@ from chromevol_enhanced_b200 import _build  # noqa: E402
 path = sys.argv[1] if len(sys.argv) > 1 else _build.LIB_PATH
 sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
 demangle = lambda n: subprocess.run(["cu++filt", n], capture_output=True, text=True).stdout.strip() or n
-KEY = ["DMMA.8x8x4", "UBLKCP", "UBLKPF", "SYNCS", "LDS", "STS", "LDG", "STG", "DADD", "DFMA", "DMUL",
+KEY = ["DMMA.8x8x4", "HMMA", "UBLKCP", "UBLKPF", "SYNCS", "LDS", "STS", "LDG", "STG", "DADD", "DFMA", "DMUL",
        "BAR", "NANOSLEEP", "ATOM", "RED"]
 kernels = collections.OrderedDict()
 cur = None
